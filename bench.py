@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark (BASELINE.json): 4-bit Llama-7B linear-layer tokens/s at bs=1 on B200,
+and the decode GEMV's achieved HBM GB/s against the measured roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one decoded token's worth of the hot path: the 224 quantised Linear layers of Llama-7B
+(32 x [q,k,v,o: 4096->4096, gate,up: 4096->11008, down: 11008->4096]), 4-bit, group 128, symmetric, fp16, M=1,
+each through `q_linear_cuda.mpq_forward` (the reference-facing plugin function) -> C ABI -> sm_100a kernels,
+captured once into a CUDA graph.  Every layer has its own weights (3.4 GB total, far larger than the 126 MB L2, so
+every step streams them from HBM; no explicit L2 flush is needed).
+
+Keys (see the task contract): value = whole-job tokens/s with inputs resident in HBM; e2e = same metric with the
+activation coming from pinned host memory and the result read back every step; roofline = algorithmic bytes per
+launch / CUDA-event time per launch against MEASURED_PEAKS.json; cpu_baseline = the reference's CPU path
+(dequantise-with-torch-ops + matmul, oracle/torch_cpu.py port) timed on the host cores for one decoder layer.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LLAMA7B = dict(hidden=4096, inter=11008, layers=32)
+W_BIT, GROUP = 4, 128
+METRIC = "llama7b_w4g128_linear_decode_tokens_per_s_bs1"
+
+
+def layer_shapes(cfg):
+    h, i = cfg["hidden"], cfg["inter"]
+    return [("q", h, h), ("k", h, h), ("v", h, h), ("o", h, h), ("gate", h, i), ("up", h, i), ("down", i, h)]
+
+
+def algorithmic_bytes(K, N, M=1, w_bit=W_BIT, group=GROUP):
+    """packed W + fp16 scales + fp16 zeros + x + y."""
+    return K * N * w_bit // 8 + 2 * (K // group) * N * 2 + 2 * M * K + 2 * M * N
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU-capable path (port), one decoder layer per step
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_layer_inputs(seed=0):
+    import torch
+    g = torch.Generator().manual_seed(1234 + seed)
+    out = []
+    for name, K, N in layer_shapes(LLAMA7B):
+        qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (K * W_BIT // 32, N), dtype=torch.int32, generator=g)
+        sc = (torch.rand((K // GROUP, N), generator=g) * 0.01 + 0.005).half()
+        zr = (sc.float() * 8).half()
+        gi = (torch.arange(K, dtype=torch.int32) // GROUP)
+        x = torch.randn((1, K), generator=g).half()
+        out.append((name, K, N, qw, sc, zr, gi, x))
+    return out
+
+
+def cpu_step(inputs):
+    """One decoder layer (7 linears) through the port of the reference CPU path: dequantise every call, as the
+    reference does (mpq_layer.py:59-63), fp32 matmul (CPU half matmul is not what a CPU user would run)."""
+    from oracle import torch_cpu
+    ys = []
+    for name, K, N, qw, sc, zr, gi, x in inputs:
+        w = torch_cpu.dequant(qw, sc, zr, gi, W_BIT, False)
+        ys.append(torch_cpu.mpq_forward(x.float(), None, None, None, None, W_BIT, False, cached_weight=w.float()))
+    return ys
+
+
+def run_cpu_arm(steps, warmup):
+    import torch
+    cores = torch.get_num_threads()
+    inputs = cpu_layer_inputs()
+    for _ in range(warmup):
+        cpu_step(inputs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(inputs)
+    dt = (time.perf_counter() - t0) / steps
+    tok_s = 1.0 / (dt * LLAMA7B["layers"])
+    sample = (f"{steps} timed passes over ONE decoder layer (7 linears, 1/32 of a token): dequantise-with-torch-ops + "
+              f"fp32 matmul per call; tokens/s = 1/(32 x layer time); layer time {dt * 1e3:.1f} ms")
+    return tok_s, cores, sample, dt
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def build_model(device, seed):
+    import torch
+    g = torch.Generator(device=device).manual_seed(1234 + seed)
+    layers = []
+    for li in range(LLAMA7B["layers"]):
+        for name, K, N in layer_shapes(LLAMA7B):
+            qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (K * W_BIT // 32, N), dtype=torch.int32, device=device,
+                               generator=g)
+            sc = (torch.rand((K // GROUP, N), device=device, generator=g) * 0.01 + 0.005).half()
+            zr = (sc.float() * 8 + torch.randn((K // GROUP, N), device=device, generator=g) * 1e-3).half()
+            gi = (torch.arange(K, dtype=torch.int32, device=device) // GROUP)
+            layers.append((name, K, N, qw, sc, zr, gi))
+    return layers
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("B200BIT_PDL", "1")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = min(args.steps, 8)
+        warm = 1
+        tok_s, cores, sample, dt = run_cpu_arm(steps, warm)
+        line = {"impl": "reference", "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3 * LLAMA7B["layers"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "llama7b_linear_layers_decode_bs1_w4_g128_sym (reference CPU path: "
+                                       "unpack_qweight-style dequant + matmul)", "requested_steps": args.steps},
+                "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": cores, "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from bitorch_engine_b200 import _cabi
+    from bitorch_engine_b200.extensions import q_linear_cuda
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    tune = os.environ.get("B200BIT_TUNE")
+    if tune:
+        L, wps, sk = (int(v) for v in tune.split(","))
+        _cabi.check(_cabi.lib().b200bit_set_gemv_tuning(L, wps, sk))
+
+    layers = build_model(dev, seed=rank)
+    h, inter = LLAMA7B["hidden"], LLAMA7B["inter"]
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    x_h = torch.randn((1, h), device=dev, generator=g).half()
+    x_i = torch.randn((1, inter), device=dev, generator=g).half()
+    pdl = bool(args.pdl)
+
+    def token_pass():
+        y = None
+        for name, K, N, qw, sc, zr, gi in layers:
+            y = q_linear_cuda.mpq_forward(x_h if K == h else x_i, qw, sc, zr, gi, 16, W_BIT, False, pdl=pdl)
+        return y
+
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        token_pass()                      # eager warm-up: g_idx verdict cache, workspace, module load
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            y_out = token_pass()
+    torch.cuda.synchronize()
+    n_launch = len(layers)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            graph.replay()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            graph.replay()
+        e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- end-to-end: pinned host x -> H2D -> graph -> D2H y, every step ----------------
+    x_host = torch.randn((1, h)).half().pin_memory()
+    y_host = torch.empty((1, h), dtype=torch.float16).pin_memory()
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            x_h.copy_(x_host, non_blocking=True); graph.replay(); y_host.copy_(y_out, non_blocking=True)
+            stream.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for _ in range(args.steps):
+            x_h.copy_(x_host, non_blocking=True)
+            graph.replay()
+            y_host.copy_(y_out, non_blocking=True)
+            stream.synchronize()          # the caller needs the token's result before the next step
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_step = ms / args.steps
+        tok_s = world * args.steps / (ms / 1e3)
+        e2e_tok_s = world * args.steps / (ms_e2e / 1e3)
+        tok_bytes = sum(algorithmic_bytes(K, N) for _, K, N, *_ in layers)
+        peak, peak_src = hbm_peak()
+        per_launch_us = ms_step * 1e3 / n_launch
+        achieved = tok_bytes / (ms_step / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_latest.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": {"workload": "llama7b_linear_layers_decode_bs1_w4_g128_sym", "layers_per_step": n_launch,
+                           "weights_bytes": tok_bytes, "l2_policy": "inputs (3.4 GB of distinct weights per step) "
+                           "larger than L2", "parallelism": f"replicas x{world}", "pdl": int(pdl),
+                           "tuning": tune or "heuristic", "cuda_graph": True},
+                "gpu_launches": n_launch * args.steps,
+                "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": x_host.numel() * 2,
+                        "d2h_bytes_per_step": y_host.numel() * 2},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "kernel": "mpq_gemv_kernel<4,f16,M=1>", "avg_launch_us": per_launch_us,
+                             "algorithmic_bytes_per_launch": tok_bytes / n_launch},
+                "clocks": clocks}
+        if not args.no_cpu_baseline and world == 1:
+            tok_cpu, cores, sample, _ = run_cpu_arm(2, 1)
+            line["cpu_baseline"] = {"value": tok_cpu, "unit": "tokens/s", "cores": cores, "kind": "port",
+                                    "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

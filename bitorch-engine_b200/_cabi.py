@@ -1,0 +1,93 @@
+"""ctypes binding of libb200bit.so (C ABI declared in include/b200bit.h).
+
+The library is the product: if it is missing or a symbol is absent this module raises -- it never falls back to
+PyTorch or to the oracle.  ctypes releases the GIL around every call (SURVEY.md section 8b "Threading")."""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200bit.so")
+
+F32, F16, BF16 = 0, 1, 2
+FLAG_PDL = 1
+WS_TICKET_BYTES = 16384
+
+_c_int, _c_size_t, _c_void_p, _c_uint = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_uint
+
+# name -> (restype, argtypes); mirrors include/b200bit.h one to one (tests/test_cabi_symbols.py checks both ways)
+PROTOTYPES = {
+    "b200bit_version": (_c_int, []),
+    "b200bit_last_error": (ctypes.c_char_p, []),
+    "b200bit_device_info": (_c_int, [ctypes.POINTER(_c_int)] * 3),
+    "b200bit_set_gemv_tuning": (_c_int, [_c_int, _c_int, _c_int]),
+    "b200bit_mpq_forward_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
+    "b200bit_mpq_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                     _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                     _c_void_p, _c_size_t, _c_uint, _c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises RuntimeError if the CUDA library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"b200bit: {LIB_PATH} is missing -- build it with `python bitorch-engine_b200/build.py` "
+                    "(there is no CPU / PyTorch fallback for this path)")
+            handle = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(handle, name)      # AttributeError if the symbol is not exported
+                fn.restype, fn.argtypes = res, args
+            _lib = handle
+    return _lib
+
+
+class B200BitError(RuntimeError):
+    pass
+
+
+def check(rc):
+    """Translate a negative return code into a Python exception (the reference raised RuntimeError through
+    AT_ASSERTM / TORCH_CHECK, or killed the process with exit(); SURVEY.md section 8b "Error convention")."""
+    if rc == 0:
+        return
+    msg = lib().b200bit_last_error().decode("utf-8", "replace")
+    if rc in (-1, -2):
+        raise ValueError(f"b200bit: {msg}")
+    if rc == -3:
+        raise NotImplementedError(f"b200bit: {msg}")
+    raise B200BitError(f"b200bit (code {rc}): {msg}")
+
+
+def dtype_code(dtype):
+    import torch
+    if dtype == torch.float16:
+        return F16
+    if dtype == torch.bfloat16:
+        return BF16
+    if dtype == torch.float32:
+        return F32
+    raise NotImplementedError(f"b200bit: tensor type not supported: {dtype}")
+
+
+_workspaces = {}
+
+
+def workspace(device, stream_ptr, nbytes):
+    """Per (device, stream) scratch: split-K partials + self-resetting tickets.  Zero-initialised once; grown on
+    demand (never inside a CUDA-graph capture: warm up first)."""
+    import torch
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws

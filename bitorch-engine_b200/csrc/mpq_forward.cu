@@ -1,0 +1,306 @@
+// mpq_forward.cu -- C-ABI entry b200bit_mpq_forward: validation, path selection (decode GEMV / batched GEMM /
+// general fallback) and the general fallback kernel.
+//
+// Reference path replaced: q_linear_cuda.mpq_forward -> mpq_linear_cuda_forward -> quantmatmul_cuda
+// (bitorch_engine/layers/qlinear/nbit/cuda/q_linear_cuda.cpp:258-270, mpq_linear_cuda_kernel.cu:603-626, 482-577).
+#include "mpq_gemv.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace b200bit {
+
+// ---------------------------------------------------------------------------------------------------------------
+// error plumbing / device info
+// ---------------------------------------------------------------------------------------------------------------
+char* err_buf() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// process-wide tuning override for sweeps (0 = heuristic); set through b200bit_set_gemv_tuning()
+static int g_tune_L = 0, g_tune_warps = 0, g_tune_splitk = 0;
+
+// ---------------------------------------------------------------------------------------------------------------
+// General fallback: any g_idx (act-order), any dtype incl. f32, any N / group size.  One thread per column,
+// fp32 math on the exact model (s*q - z), M tiled by 4 through gridDim.y.  Correctness path, not a fast path.
+// ---------------------------------------------------------------------------------------------------------------
+template <int DT>
+__device__ __forceinline__ float load_el(const void* p, size_t i) {
+    if constexpr (DT == B200BIT_F32) return reinterpret_cast<const float*>(p)[i];
+    else if constexpr (DT == B200BIT_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+    else return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+template <int DT>
+__device__ __forceinline__ void store_el(void* p, size_t i, float v) {
+    if constexpr (DT == B200BIT_F32) reinterpret_cast<float*>(p)[i] = v;
+    else if constexpr (DT == B200BIT_F16) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(128) mpq_general_kernel(const void* __restrict__ x, const uint32_t* __restrict__ qw,
+                                                          const void* __restrict__ scales,
+                                                          const void* __restrict__ zeros,
+                                                          const int32_t* __restrict__ g_idx, void* __restrict__ y,
+                                                          int M, int K, int N, int G, int w_bit, int asym) {
+    pdl_launch_dependents();
+    pdl_wait_primary();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m0 = blockIdx.y * 4;
+    const int mc = min(4, M - m0);
+    if (n >= N) return;
+    const int nb = 32 / w_bit;
+    const uint32_t mask = (w_bit == 32) ? 0xffffffffu : ((1u << w_bit) - 1u);
+    const int gs = K / G;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int R = K / nb;
+    int g_prev = -1;
+    float s = 0.f, z = 0.f;
+    for (int r = 0; r < R; ++r) {
+        const uint32_t w = qw[size_t(r) * N + n];
+        for (int j = 0; j < nb; ++j) {
+            const int k = r * nb + j;
+            const int g = g_idx ? g_idx[k] : k / gs;
+            if (g != g_prev) {
+                s = load_el<DT>(scales, size_t(g) * N + n);
+                if (asym) {
+                    const uint32_t zw = reinterpret_cast<const uint32_t*>(zeros)[size_t(g) * (N / nb) + n / nb];
+                    z = s * float(((zw >> ((n % nb) * w_bit)) & mask) + 1u);
+                } else {
+                    z = load_el<DT>(zeros, size_t(g) * N + n);
+                }
+                g_prev = g;
+            }
+            const float wv = fmaf(s, float((w >> (j * w_bit)) & mask), -z);
+            for (int m = 0; m < mc; ++m) acc[m] = fmaf(load_el<DT>(x, size_t(m0 + m) * K + k), wv, acc[m]);
+        }
+    }
+    for (int m = 0; m < mc; ++m) store_el<DT>(y, size_t(m0 + m) * N + n, acc[m]);
+}
+
+static int launch_general(const void* x, const int32_t* qw, const void* scales, const void* zeros,
+                          const int32_t* g_idx, void* y, int M, int K, int N, int G, int w_bit, int asym, int dtype,
+                          unsigned flags, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((N + 127) / 128, (M + 3) / 4, 1);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (flags & B200BIT_FLAG_PDL) ? 1 : 0;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(qw);
+    switch (dtype) {
+        case B200BIT_F32:
+            B200_CUDA_OK(cudaLaunchKernelEx(&cfg, mpq_general_kernel<B200BIT_F32>, x, q, scales, zeros, g_idx, y, M, K,
+                                            N, G, w_bit, asym));
+            break;
+        case B200BIT_F16:
+            B200_CUDA_OK(cudaLaunchKernelEx(&cfg, mpq_general_kernel<B200BIT_F16>, x, q, scales, zeros, g_idx, y, M, K,
+                                            N, G, w_bit, asym));
+            break;
+        default:
+            B200_CUDA_OK(cudaLaunchKernelEx(&cfg, mpq_general_kernel<B200BIT_BF16>, x, q, scales, zeros, g_idx, y, M,
+                                            K, N, G, w_bit, asym));
+    }
+    return B200BIT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// decode GEMV launch plan
+// ---------------------------------------------------------------------------------------------------------------
+struct GemvPlan {
+    bool ok;
+    int FR, L_log2, warps, splitk, runs_total, runs_per_split, rpr, rpr_shift;
+    size_t smem;
+};
+
+static size_t gemv_smem_bytes(int M, int nb, int nruns, int FR, int warps, int L) {
+    const size_t xs = size_t(M) * nruns * (GEMV_RUN * nb + 8) * 2;
+    const size_t xseg = size_t((M * nruns * (GEMV_RUN / FR) + 3) & ~3) * 4;
+    return xs + xseg + size_t(warps) * M * 4 * L * 4;
+}
+
+static GemvPlan plan_gemv(int M, int K, int N, int G, int w_bit, int asym, int dtype, bool trivial_gidx) {
+    GemvPlan pl{};
+    pl.ok = false;
+    if (!trivial_gidx || dtype == B200BIT_F32) return pl;
+    if (dtype == B200BIT_BF16 && w_bit > 4) return pl;
+    const int nb = 32 / w_bit;
+    if (K % (nb * GEMV_RUN) != 0 || K % G != 0) return pl;      // whole runs only
+    if (asym && N % nb != 0) return pl;
+    const int gs = K / G;
+    if (gs % nb != 0) return pl;
+    const int rpg = gs / nb;
+    if (rpg >= GEMV_RUN) {
+        if (rpg % GEMV_RUN != 0) return pl;                     // runs would straddle groups
+        pl.FR = GEMV_RUN;
+        pl.rpr = rpg / GEMV_RUN;
+        pl.rpr_shift = -1;
+        for (int sh = 0; sh < 30; ++sh) if ((1 << sh) == pl.rpr) pl.rpr_shift = sh;
+    } else {
+        if (GEMV_RUN % rpg != 0) return pl;
+        pl.FR = rpg;
+        pl.rpr = 1;
+        pl.rpr_shift = 0;
+    }
+    const int R = K / nb;
+    pl.runs_total = R / GEMV_RUN;
+    // lanes per row segment: widest tuned/default value whose strip width divides N
+    int L = g_tune_L ? g_tune_L : 8;
+    while (L > 8 && N % (4 * L) != 0) L >>= 1;
+    if (N % (4 * L) != 0) return pl;
+    pl.L_log2 = L == 32 ? 5 : L == 16 ? 4 : 3;
+    const int LG = 32 / L;
+    pl.warps = g_tune_warps ? g_tune_warps : 8;
+    const int slots = pl.warps * LG;
+    const int strips = N / (4 * L);
+    int splitk;
+    if (g_tune_splitk) {
+        splitk = g_tune_splitk;
+    } else {
+        const int want = (3 * sm_count() + strips - 1) / strips;                  // ~3 CTAs per SM
+        const int most = pl.runs_total / slots > 0 ? pl.runs_total / slots : 1;   // >= one run per slot
+        splitk = want < most ? want : most;
+    }
+    if (splitk < 1) splitk = 1;
+    if (splitk > pl.runs_total) splitk = pl.runs_total;
+    if (splitk > 64) splitk = 64;
+    // bound shared memory (x chunk) by splitting K further
+    for (;; ++splitk) {
+        pl.runs_per_split = (pl.runs_total + splitk - 1) / splitk;
+        pl.smem = gemv_smem_bytes(M, nb, pl.runs_per_split, pl.FR, pl.warps, L);
+        if (pl.smem <= 160 * 1024 || splitk >= pl.runs_total || splitk >= 64) break;
+    }
+    pl.splitk = (pl.runs_total + pl.runs_per_split - 1) / pl.runs_per_split;
+    pl.ok = pl.smem <= 200 * 1024;
+    return pl;
+}
+
+static int launch_gemv(const GemvParams& p, const GemvLaunch& l, int w_bit, bool bf16) {
+    switch (w_bit) {
+        case 1: return bf16 ? launch_gemv_family<1, true>(p, l) : launch_gemv_family<1, false>(p, l);
+        case 2: return bf16 ? launch_gemv_family<2, true>(p, l) : launch_gemv_family<2, false>(p, l);
+        case 4: return bf16 ? launch_gemv_family<4, true>(p, l) : launch_gemv_family<4, false>(p, l);
+        case 8: if (!bf16) return launch_gemv_family<8, false>(p, l);
+    }
+    return set_error(B200BIT_ERR_UNSUPPORTED, "gemv: w_bit=%d bf16=%d", w_bit, int(bf16));
+}
+
+}  // namespace b200bit
+
+using namespace b200bit;
+
+extern "C" {
+
+int b200bit_version(void) { return B200BIT_VERSION; }
+const char* b200bit_last_error(void) { return err_buf(); }
+
+int b200bit_device_info(int* sm, int* major, int* minor) {
+    int dev = 0;
+    B200_CUDA_OK(cudaGetDevice(&dev));
+    if (sm) B200_CUDA_OK(cudaDeviceGetAttribute(sm, cudaDevAttrMultiProcessorCount, dev));
+    if (major) B200_CUDA_OK(cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (minor) B200_CUDA_OK(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return B200BIT_OK;
+}
+
+/* sweep hook (bench / tests only): lanes per row segment (8/16/32), warps per CTA, split-K; 0 = heuristic */
+int b200bit_set_gemv_tuning(int L, int warps, int splitk) {
+    B200_REQUIRE(L == 0 || L == 8 || L == 16 || L == 32, B200BIT_ERR_ARG, "L must be 0, 8, 16 or 32");
+    B200_REQUIRE(warps >= 0 && warps <= 16, B200BIT_ERR_ARG, "warps must be in [0,16]");
+    B200_REQUIRE(splitk >= 0, B200BIT_ERR_ARG, "splitk must be >= 0");
+    g_tune_L = L; g_tune_warps = warps; g_tune_splitk = splitk;
+    return B200BIT_OK;
+}
+
+size_t b200bit_mpq_forward_workspace_bytes(int M, int K, int N, int w_bit) {
+    (void)K; (void)w_bit;
+    const int mm = M < GEMV_MAX_M ? M : GEMV_MAX_M;
+    // tickets | split-K partials (<= 64 splits of [mm, N] f32)
+    return size_t(B200BIT_WS_TICKET_BYTES) + size_t(64) * mm * N * sizeof(float);
+}
+
+int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scales, const void* zeros,
+                        const int32_t* g_idx, void* y, int M, int K, int N, int G, int w_bit, int asym, int dtype,
+                        void* workspace, size_t workspace_bytes, unsigned flags, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    B200_REQUIRE(x && qweight && scales && zeros && y, B200BIT_ERR_ARG, "mpq_forward: null pointer argument");
+    B200_REQUIRE(dtype == B200BIT_F32 || dtype == B200BIT_F16 || dtype == B200BIT_BF16, B200BIT_ERR_ARG,
+                 "mpq_forward: bad dtype code %d", dtype);
+    B200_REQUIRE(w_bit == 1 || w_bit == 2 || w_bit == 4 || w_bit == 8, B200BIT_ERR_UNSUPPORTED,
+                 "mpq_forward: w_bit=%d not supported (1, 2, 4, 8)", w_bit);
+    B200_REQUIRE(M >= 0 && K > 0 && N > 0 && G > 0, B200BIT_ERR_SHAPE, "mpq_forward: bad sizes M=%d K=%d N=%d G=%d", M,
+                 K, N, G);
+    const int nb = 32 / w_bit;
+    B200_REQUIRE(K % nb == 0, B200BIT_ERR_SHAPE, "mpq_forward: K=%d must be a multiple of %d", K, nb);
+    B200_REQUIRE(g_idx || K % G == 0, B200BIT_ERR_SHAPE, "mpq_forward: K=%d not divisible by G=%d", K, G);
+    B200_REQUIRE(!asym || N % nb == 0, B200BIT_ERR_SHAPE, "mpq_forward: asym needs N %% %d == 0 (N=%d)", nb, N);
+    if (M == 0) return B200BIT_OK;
+
+    const GemvPlan pl = plan_gemv(M < GEMV_MAX_M ? M : GEMV_MAX_M, K, N, G, w_bit, asym, dtype, g_idx == nullptr);
+    const int max_m = (w_bit == 2 || w_bit == 4) ? GEMV_MAX_M : 1;
+    if (!pl.ok) return launch_general(x, qweight, scales, zeros, g_idx, y, M, K, N, G, w_bit, asym, dtype, flags, stream);
+
+    float* ws_part = nullptr;
+    unsigned* tickets = nullptr;
+    if (pl.splitk > 1) {
+        const int L = 1 << pl.L_log2;
+        const size_t strips = N / (4 * L);
+        const int mm = M < max_m ? M : max_m;
+        const size_t need = size_t(B200BIT_WS_TICKET_BYTES) + size_t(pl.splitk) * mm * N * sizeof(float);
+        B200_REQUIRE(workspace && workspace_bytes >= need, B200BIT_ERR_WORKSPACE,
+                     "mpq_forward: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+        B200_REQUIRE(strips * sizeof(unsigned) <= B200BIT_WS_TICKET_BYTES, B200BIT_ERR_SHAPE,
+                     "mpq_forward: N=%d too large for the ticket area", N);
+        tickets = reinterpret_cast<unsigned*>(workspace);
+        ws_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B200BIT_WS_TICKET_BYTES);
+    }
+    for (int m0 = 0; m0 < M; m0 += max_m) {
+        const int mc = (M - m0) < max_m ? (M - m0) : max_m;
+        GemvParams p{};
+        p.x = reinterpret_cast<const uint16_t*>(x) + size_t(m0) * K;
+        p.qw = reinterpret_cast<const uint32_t*>(qweight);
+        p.scales = reinterpret_cast<const uint16_t*>(scales);
+        p.zeros = zeros;
+        p.y = reinterpret_cast<uint16_t*>(y) + size_t(m0) * N;
+        p.ws_part = ws_part;
+        p.tickets = tickets;
+        p.K = K; p.N = N; p.R = K / nb; p.G = G;
+        p.rpr = pl.rpr;
+        p.rpr_shift = pl.rpr_shift;
+        p.runs_total = pl.runs_total;
+        p.runs_per_split = pl.runs_per_split;
+        p.L_log2 = pl.L_log2;
+        p.asym = asym;
+        GemvLaunch l{};
+        l.M = mc; l.FR = pl.FR; l.warps = pl.warps; l.splitk = pl.splitk;
+        l.smem = gemv_smem_bytes(mc, nb, pl.runs_per_split, pl.FR, pl.warps, 1 << pl.L_log2);
+        l.flags = flags; l.stream = stream;
+        const int rc = launch_gemv(p, l, w_bit, dtype == B200BIT_BF16);
+        if (rc != B200BIT_OK) return rc;
+    }
+    return B200BIT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference Python
+(/root/reference/bitorch_engine) on CPU in the build container.  /root/reference does not exist on the GPU box, so
+the vectors are committed; re-run this script to regenerate them:
+
+    python oracle/gen_golden.py            # writes tests/golden/nbit_cases.npz, ...
+
+What runs from the reference (nothing is copied, only imported):
+  * bitorch_engine/layers/qlinear/nbit/cuda/utils.py: unpack_qweight (5-69), pack_fp_weight (72-147)
+  * bitorch_engine/utils/quant_operators.py: gptq_style_unpacking (310-345), gptq_style_zeros_packing (348-368)
+  * bitorch_engine/utils/model_helper.py: qweight_update_fn (363-530)
+  * bitorch_engine/optim/diode_beta.py: DiodeMix
+The un-vendored `bitorch` dependency is satisfied by the import-only stub in oracle/_stubs.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+os.environ["BIE_SKIP_TORCH_CHECK"] = "true"
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_stubs"))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+TORCH_DT = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}
+
+
+def _bits(t):
+    """torch half/bf16 -> uint16 numpy bits; float32 -> float32 numpy."""
+    if t.dtype in (torch.float16, torch.bfloat16):
+        return t.contiguous().view(torch.int16).numpy().view(np.uint16)
+    return t.contiguous().numpy()
+
+
+def make_inputs(K, N, w_bit, group, dt, asym, act_order, seed):
+    """Synthetic inputs per SURVEY.md section 8(d)."""
+    g = torch.Generator().manual_seed(seed)
+    tdt = TORCH_DT[dt]
+    nb = 32 // w_bit
+    G = K // group
+    qweight = torch.randint(-2 ** 31, 2 ** 31 - 1, (K // nb, N), dtype=torch.int32, generator=g)
+    scales = (torch.rand((G, N), generator=g) * 0.01 + 0.005).to(tdt)
+    if asym:
+        zeros = torch.randint(-2 ** 31, 2 ** 31 - 1, (G, N // nb), dtype=torch.int32, generator=g)
+    else:
+        zeros = (scales.float() * (2 ** (w_bit - 1)) + torch.randn((G, N), generator=g) * 1e-3).to(tdt)
+    g_idx = torch.arange(K, dtype=torch.int32) // group
+    if act_order:
+        g_idx = g_idx[torch.randperm(K, generator=g)].contiguous()
+    x = torch.randn((3, K), generator=g).to(tdt)
+    dy = torch.randn((3, N), generator=g).to(tdt)
+    return qweight, scales, zeros, g_idx, x, dy
+
+
+def gen_nbit():
+    from bitorch_engine.layers.qlinear.nbit import MPQWeightParameter
+    from bitorch_engine.layers.qlinear.nbit.cuda.utils import unpack_qweight, pack_fp_weight
+
+    out = {}
+    cases = []
+    K, N = 256, 64
+    cid = 0
+    for w_bit in (4, 2, 8, 1):
+        for dt in ("f16", "bf16", "f32"):
+            if w_bit in (8, 1) and dt != "f16":
+                continue
+            for asym in (False, True):
+                for act_order in (False, True):
+                    if w_bit in (8, 1) and act_order:
+                        continue
+                    group = 32 if w_bit == 2 else 128
+                    seed = 1000 + cid
+                    qweight, scales, zeros, g_idx, x, dy = make_inputs(K, N, w_bit, group, dt, asym, act_order, seed)
+                    qp = MPQWeightParameter(qweight.clone(), requires_grad=False, scales=scales, zeros=zeros,
+                                            g_idx=g_idx, w_bit=w_bit, asym=asym, group_size=group, layer_type=1)
+                    W = unpack_qweight(qp)                      # reference, dtype = scales dtype
+                    assert W.dtype == TORCH_DT[dt], (W.dtype, dt)
+                    y = x.float() @ W.float()                  # the tight oracle
+                    dx = dy.float() @ W.float().t()
+                    # pack: a perturbed weight so rounding / clamping paths are exercised
+                    gen = torch.Generator().manual_seed(seed + 7)
+                    Wp = (W.float() + torch.randn(W.shape, generator=gen) * 0.02).to(W.dtype)
+                    packed = pack_fp_weight(Wp, qp)
+                    roundtrip = pack_fp_weight(W, qp)
+                    name = f"c{cid}"
+                    cases.append((name, w_bit, dt, int(asym), int(act_order), group, K, N))
+                    out[f"{name}_qweight"] = qweight.numpy()
+                    out[f"{name}_scales"] = _bits(scales)
+                    out[f"{name}_zeros"] = _bits(zeros) if not asym else zeros.numpy()
+                    out[f"{name}_g_idx"] = g_idx.numpy()
+                    out[f"{name}_x"] = _bits(x)
+                    out[f"{name}_dy"] = _bits(dy)
+                    out[f"{name}_W"] = _bits(W)
+                    out[f"{name}_y"] = y.numpy()
+                    out[f"{name}_dx"] = dx.numpy()
+                    out[f"{name}_Wp"] = _bits(Wp)
+                    out[f"{name}_packed"] = packed.numpy()
+                    out[f"{name}_roundtrip_equal"] = np.array(int(torch.equal(roundtrip, qweight)))
+                    cid += 1
+    out["cases"] = np.array([",".join(map(str, c)) for c in cases])
+    os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, "nbit_cases.npz"), **out)
+    print(f"nbit: {len(cases)} cases -> tests/golden/nbit_cases.npz")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["nbit"]
+    for w in what:
+        globals()[f"gen_{w}"]()
