@@ -4,6 +4,7 @@
 // Reference path replaced: q_linear_cuda.mpq_forward -> mpq_linear_cuda_forward -> quantmatmul_cuda
 // (bitorch_engine/layers/qlinear/nbit/cuda/q_linear_cuda.cpp:258-270, mpq_linear_cuda_kernel.cu:603-626, 482-577).
 #include "mpq_gemv.cuh"
+#include "mpq_mma.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -38,6 +39,10 @@ int sm_count() {
 
 // process-wide tuning override for sweeps (0 = heuristic); set through b200bit_set_gemv_tuning()
 static int g_tune_L = 0, g_tune_warps = 0, g_tune_splitk = 0;
+// 0 = auto, 1 = CUDA-core FHFMA GEMV, 2 = mma.sync small-batch kernel, 3 = general fallback
+static int g_path = 0;
+// in auto mode, does M == 1 go to the tensor kernel (1) or stay on the CUDA-core GEMV (0)?
+static int g_mma_for_m1 = 0;
 
 // ---------------------------------------------------------------------------------------------------------------
 // General fallback: any g_idx (act-order), any dtype incl. f32, any N / group size.  One thread per column,
@@ -166,23 +171,26 @@ static GemvPlan plan_gemv(int M, int K, int N, int G, int w_bit, int asym, int d
     }
     const int R = K / nb;
     pl.runs_total = R / GEMV_RUN;
-    // lanes per row segment: widest tuned/default value whose strip width divides N
-    int L = g_tune_L ? g_tune_L : 8;
+    // lanes per row segment / warps / split-K: measured on B200 (profiles/r1_gemv_sweep.md): few wide-K strips ->
+    // one 16-warp CTA per 32-column strip; many strips (N >= ~2 strips per SM) -> 64-column strips, 4 warps, split-K 4
+    const bool many_strips = (N / 32) >= 2 * sm_count();
+    int L = g_tune_L ? g_tune_L : (many_strips ? 16 : 8);
     while (L > 8 && N % (4 * L) != 0) L >>= 1;
     if (N % (4 * L) != 0) return pl;
     pl.L_log2 = L == 32 ? 5 : L == 16 ? 4 : 3;
     const int LG = 32 / L;
-    pl.warps = g_tune_warps ? g_tune_warps : 8;
+    pl.warps = g_tune_warps ? g_tune_warps : (many_strips ? 4 : 16);
     const int slots = pl.warps * LG;
     const int strips = N / (4 * L);
     int splitk;
     if (g_tune_splitk) {
         splitk = g_tune_splitk;
     } else {
-        const int want = (3 * sm_count() + strips - 1) / strips;                  // ~3 CTAs per SM
+        splitk = many_strips ? 4 : 1;
         const int most = pl.runs_total / slots > 0 ? pl.runs_total / slots : 1;   // >= one run per slot
-        splitk = want < most ? want : most;
+        if (splitk > most) splitk = most;
     }
+    (void)strips;
     if (splitk < 1) splitk = 1;
     if (splitk > pl.runs_total) splitk = pl.runs_total;
     if (splitk > 64) splitk = 64;
@@ -205,6 +213,81 @@ static int launch_gemv(const GemvParams& p, const GemvLaunch& l, int w_bit, bool
         case 8: if (!bf16) return launch_gemv_family<8, false>(p, l);
     }
     return set_error(B200BIT_ERR_UNSUPPORTED, "gemv: w_bit=%d bf16=%d", w_bit, int(bf16));
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// small-batch mma.sync launch plan
+// ---------------------------------------------------------------------------------------------------------------
+struct MmaPlan {
+    bool ok;
+    int FJ, warps, splitk, runs_total, runs_per_split, rpr, rpr_shift;
+};
+
+static size_t mma_smem_bytes(int M, int nb, int nruns, int FJ, int warps) {
+    const size_t chunk_rows = size_t(nruns) * MMA_RUN_ROWS;
+    const size_t xs = size_t(M) * (chunk_rows * nb + 32) * 2;
+    const size_t xseg = size_t((M * nruns * (MMA_U / FJ) + 3) & ~3) * 4;
+    return xs + xseg + size_t(warps) * M * 32 * 4;
+}
+
+static MmaPlan plan_mma(int M, int K, int N, int G, int w_bit, int asym, int dtype, bool trivial_gidx) {
+    MmaPlan pl{};
+    pl.ok = false;
+    if (!trivial_gidx || dtype != B200BIT_F16) return pl;
+    if (w_bit != 2 && w_bit != 4 && w_bit != 8) return pl;
+    const int nb = 32 / w_bit;
+    if (N % 32 != 0 || K % (nb * MMA_RUN_ROWS) != 0 || K % G != 0) return pl;
+    if (asym && N % nb != 0) return pl;
+    const int gs = K / G;
+    if (gs % nb != 0) return pl;
+    const int rpg = gs / nb;
+    if (rpg % 4 != 0) return pl;
+    if (rpg >= MMA_RUN_ROWS) {
+        if (rpg % MMA_RUN_ROWS != 0) return pl;
+        pl.FJ = MMA_U;
+        pl.rpr = rpg / MMA_RUN_ROWS;
+        pl.rpr_shift = -1;
+        for (int sh = 0; sh < 30; ++sh) if ((1 << sh) == pl.rpr) pl.rpr_shift = sh;
+    } else {
+        if (MMA_RUN_ROWS % rpg != 0) return pl;
+        pl.FJ = rpg / 4;
+        pl.rpr = 1;
+        pl.rpr_shift = 0;
+    }
+    pl.runs_total = (K / nb) / MMA_RUN_ROWS;
+    pl.warps = g_tune_warps ? (g_tune_warps > 8 ? 8 : g_tune_warps) : 4;
+    const int strips = N / 32;
+    int splitk;
+    if (g_tune_splitk) {
+        splitk = g_tune_splitk;
+    } else {
+        const int want = (4 * sm_count() + strips - 1) / strips;
+        const int most = pl.runs_total / pl.warps > 0 ? pl.runs_total / pl.warps : 1;
+        splitk = want < most ? want : most;
+    }
+    if (splitk < 1) splitk = 1;
+    if (splitk > pl.runs_total) splitk = pl.runs_total;
+    if (splitk > 64) splitk = 64;
+    const int mm = M < 32 ? M : 32;
+    for (;; ++splitk) {
+        pl.runs_per_split = (pl.runs_total + splitk - 1) / splitk;
+        if (mma_smem_bytes(mm, nb, pl.runs_per_split, pl.FJ, pl.warps) <= 100 * 1024 || splitk >= pl.runs_total ||
+            splitk >= 64)
+            break;
+    }
+    pl.splitk = (pl.runs_total + pl.runs_per_split - 1) / pl.runs_per_split;
+    pl.ok = mma_smem_bytes(mm, nb, pl.runs_per_split, pl.FJ, pl.warps) <= 200 * 1024;
+    return pl;
+}
+
+static int launch_mma(const MmaParams& p, const MmaLaunch& l, int w_bit) {
+    switch (w_bit) {
+        case 2: return launch_mma_family<2>(p, l);
+        case 4: return launch_mma_family<4>(p, l);
+        case 8: return launch_mma_family<8>(p, l);
+    }
+    return set_error(B200BIT_ERR_UNSUPPORTED, "mma: w_bit=%d", w_bit);
 }
 
 }  // namespace b200bit
@@ -234,9 +317,18 @@ int b200bit_set_gemv_tuning(int L, int warps, int splitk) {
     return B200BIT_OK;
 }
 
+/* path override for benchmarks/tests: 0 auto, 1 CUDA-core GEMV, 2 small-batch mma kernel, 3 general fallback;
+ * mma_for_m1: in auto mode route M == 1 to the mma kernel (1) or to the CUDA-core GEMV (0) */
+int b200bit_set_path(int path, int mma_for_m1) {
+    B200_REQUIRE(path >= 0 && path <= 3, B200BIT_ERR_ARG, "path must be in [0,3]");
+    g_path = path;
+    g_mma_for_m1 = mma_for_m1 ? 1 : 0;
+    return B200BIT_OK;
+}
+
 size_t b200bit_mpq_forward_workspace_bytes(int M, int K, int N, int w_bit) {
     (void)K; (void)w_bit;
-    const int mm = M < GEMV_MAX_M ? M : GEMV_MAX_M;
+    const int mm = M < 32 ? M : 32;
     // tickets | split-K partials (<= 64 splits of [mm, N] f32)
     return size_t(B200BIT_WS_TICKET_BYTES) + size_t(64) * mm * N * sizeof(float);
 }
@@ -258,7 +350,46 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
     B200_REQUIRE(!asym || N % nb == 0, B200BIT_ERR_SHAPE, "mpq_forward: asym needs N %% %d == 0 (N=%d)", nb, N);
     if (M == 0) return B200BIT_OK;
 
-    const GemvPlan pl = plan_gemv(M < GEMV_MAX_M ? M : GEMV_MAX_M, K, N, G, w_bit, asym, dtype, g_idx == nullptr);
+    const bool trivial = (g_idx == nullptr);
+    // ---- path selection: small-batch tensor kernel (f16) > CUDA-core GEMV (f16/bf16, M <= 4 per pass) > general ----
+    const MmaPlan mp = (g_path == 0 || g_path == 2) ? plan_mma(M, K, N, G, w_bit, asym, dtype, trivial) : MmaPlan{};
+    if (mp.ok && !(g_path == 0 && M == 1 && !g_mma_for_m1)) {
+        float* part = nullptr;
+        unsigned* tick = nullptr;
+        const int mm = M < 32 ? M : 32;
+        if (mp.splitk > 1) {
+            const size_t need = size_t(B200BIT_WS_TICKET_BYTES) + size_t(mp.splitk) * mm * N * sizeof(float);
+            B200_REQUIRE(workspace && workspace_bytes >= need, B200BIT_ERR_WORKSPACE,
+                         "mpq_forward: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+            B200_REQUIRE(size_t(N / 32) * sizeof(unsigned) <= B200BIT_WS_TICKET_BYTES, B200BIT_ERR_SHAPE,
+                         "mpq_forward: N=%d too large for the ticket area", N);
+            tick = reinterpret_cast<unsigned*>(workspace);
+            part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B200BIT_WS_TICKET_BYTES);
+        }
+        for (int m0 = 0; m0 < M; m0 += 32) {
+            const int mc = (M - m0) < 32 ? (M - m0) : 32;
+            MmaParams p{};
+            p.x = reinterpret_cast<const uint16_t*>(x) + size_t(m0) * K;
+            p.qw = reinterpret_cast<const uint32_t*>(qweight);
+            p.scales = reinterpret_cast<const uint16_t*>(scales);
+            p.zeros = zeros;
+            p.y = reinterpret_cast<uint16_t*>(y) + size_t(m0) * N;
+            p.ws_part = part; p.tickets = tick;
+            p.M = mc; p.K = K; p.N = N; p.R = K / nb; p.G = G;
+            p.runs_total = mp.runs_total; p.runs_per_split = mp.runs_per_split;
+            p.rpr = mp.rpr; p.rpr_shift = mp.rpr_shift; p.asym = asym;
+            MmaLaunch l{};
+            l.MT = (mc + 7) / 8; l.FJ = mp.FJ; l.warps = mp.warps; l.splitk = mp.splitk;
+            l.smem = mma_smem_bytes(mc, nb, mp.runs_per_split, mp.FJ, mp.warps);
+            l.flags = flags; l.stream = stream;
+            const int rc = launch_mma(p, l, w_bit);
+            if (rc != B200BIT_OK) return rc;
+        }
+        return B200BIT_OK;
+    }
+
+    const GemvPlan pl = (g_path == 3 || g_path == 2) ? GemvPlan{} :
+        plan_gemv(M < GEMV_MAX_M ? M : GEMV_MAX_M, K, N, G, w_bit, asym, dtype, trivial);
     const int max_m = (w_bit == 2 || w_bit == 4) ? GEMV_MAX_M : 1;
     if (!pl.ok) return launch_general(x, qweight, scales, zeros, g_idx, y, M, K, N, G, w_bit, asym, dtype, flags, stream);
 

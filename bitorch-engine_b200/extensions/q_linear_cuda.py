@@ -4,9 +4,6 @@ import torch
 
 from .. import _cabi
 
-_trivial_gidx_cache = {}
-
-
 def _check_cuda(t, name):
     # reference: CHECK_CUDA -> AT_ASSERTM -> RuntimeError (q_linear_cuda.cpp:255-256)
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
@@ -15,22 +12,21 @@ def _check_cuda(t, name):
 
 def _gidx_is_trivial(g_idx, K, G):
     """True when g_idx == arange(K) // (K // G) (nbit/layer.py:385-386), i.e. groups are contiguous: the fast
-    kernels then derive the group from k and never read g_idx.  Checked once per tensor version (one D2H sync),
-    cached afterwards so steady-state calls stay asynchronous / graph-capturable."""
+    kernels then derive the group from k and never read g_idx.  Checked once per tensor object and version (one
+    D2H sync) and remembered ON the tensor, so steady-state calls stay asynchronous / graph-capturable."""
     if g_idx is None:
         return True
-    key = (g_idx.data_ptr(), g_idx._version, K, G, g_idx.device.index)
-    hit = _trivial_gidx_cache.get(key)
-    if hit is None:
-        if K % G != 0 or g_idx.numel() != K:
-            hit = False
-        else:
-            ref = torch.arange(K, device=g_idx.device, dtype=g_idx.dtype) // (K // G)
-            hit = bool(torch.equal(g_idx, ref))
-        if len(_trivial_gidx_cache) > 4096:
-            _trivial_gidx_cache.clear()
-        _trivial_gidx_cache[key] = hit
-    return hit
+    tag = getattr(g_idx, "_b200bit_trivial", None)
+    key = (g_idx._version, K, G)
+    if tag is not None and tag[0] == key:
+        return tag[1]
+    if K % G != 0 or g_idx.numel() != K:
+        verdict = False
+    else:
+        ref = torch.arange(K, device=g_idx.device, dtype=g_idx.dtype) // (K // G)
+        verdict = bool(torch.equal(g_idx, ref))
+    g_idx._b200bit_trivial = (key, verdict)
+    return verdict
 
 
 def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False):
@@ -53,6 +49,8 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         raise ValueError(f"qweight must be int32 [K*w_bit/32, N]; got {tuple(qweight.shape)} for K={K}, w_bit={w_bit}")
     if scales.dtype != x.dtype:
         raise ValueError(f"scales dtype {scales.dtype} must match x dtype {x.dtype}")
+    if M == 0:
+        return torch.empty((0, N), dtype=x.dtype, device=x.device)
     x = x.contiguous()
     qweight = qweight.contiguous()
     scales = scales.contiguous()

@@ -78,6 +78,9 @@ B200BIT_API int b200bit_mpq_forward(const void* x, const int32_t* qweight, const
 /* Sweep hook for bench.py / tests (process-wide; 0 = built-in heuristic): lanes per packed-row segment (8, 16, 32),
  * warps per CTA (1..16), split-K factor of the decode GEMV.  No reference counterpart. */
 B200BIT_API int b200bit_set_gemv_tuning(int lanes_per_row, int warps, int splitk);
+/* Kernel-path override (process-wide): 0 auto, 1 CUDA-core FHFMA GEMV, 2 small-batch mma.sync kernel, 3 general
+ * fallback; mma_for_m1 selects, in auto mode, whether M == 1 uses the tensor kernel (1) or the CUDA-core GEMV (0). */
+B200BIT_API int b200bit_set_path(int path, int mma_for_m1);
 
 #ifdef __cplusplus
 }

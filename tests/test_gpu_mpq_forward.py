@@ -13,10 +13,22 @@ pytestmark = pytest.mark.gpu
 CASES = load_nbit_cases()
 
 
-def _run(inp, w_bit, asym):
+PATHS = {"auto": (0, 1), "gemv": (1, 0), "mma": (2, 1)}
+
+
+def _run(inp, w_bit, asym, path="auto"):
+    """path: auto | gemv (CUDA-core FHFMA kernel) | mma (small-batch tensor kernel); forced paths fall through to
+    the general kernel when a configuration is outside their envelope, which is still a valid parity check."""
+    from bitorch_engine_b200 import _cabi
     from bitorch_engine_b200.extensions import q_linear_cuda
-    y = q_linear_cuda.mpq_forward(inp["x"], inp["qweight"], inp["scales"], inp["zeros"], inp["g_idx"], 16, w_bit, asym)
-    torch.cuda.synchronize()
+    lib = _cabi.lib()
+    lib.b200bit_set_path(*PATHS[path])
+    try:
+        y = q_linear_cuda.mpq_forward(inp["x"], inp["qweight"], inp["scales"], inp["zeros"], inp["g_idx"], 16, w_bit,
+                                      asym)
+        torch.cuda.synchronize()
+    finally:
+        lib.b200bit_set_path(0, 1)
     return y
 
 
@@ -46,10 +58,11 @@ LLAMA = [(4096, 4096), (4096, 11008), (11008, 4096)]
 
 
 @pytest.mark.parametrize("K,N", LLAMA)
-@pytest.mark.parametrize("M", [1, 2, 4])
-def test_llama7b_shapes_4bit_g128(K, N, M):
+@pytest.mark.parametrize("M", [1, 2, 4, 8, 32])
+@pytest.mark.parametrize("path", ["gemv", "mma"])
+def test_llama7b_shapes_4bit_g128(K, N, M, path):
     inp = make_mpq_inputs(K, N, 4, 128, "f16", False, M=M, seed=K + N + M, device="cuda")
-    y = _run(inp, 4, False)
+    y = _run(inp, 4, False, path)
     y_ref, y_exact = _oracles(inp, 4, False, "f16", None)
     assert_close_to_oracles(to_np_f32(y), y_ref, y_exact, "f16", f"{K}x{N} M={M}")
 
@@ -58,18 +71,20 @@ def test_llama7b_shapes_4bit_g128(K, N, M):
                                          (1, 32), (4, 1024)])
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
 @pytest.mark.parametrize("asym", [False, True])
-def test_bits_groups_dtypes(w_bit, group, dt, asym):
+@pytest.mark.parametrize("path", ["gemv", "mma"])
+def test_bits_groups_dtypes(w_bit, group, dt, asym, path):
     K, N, M = 2048, 1024, 1
     inp = make_mpq_inputs(K, N, w_bit, group, dt, asym, M=M, seed=w_bit * 1000 + group, device="cuda")
-    y = _run(inp, w_bit, asym)
+    y = _run(inp, w_bit, asym, path)
     y_ref, y_exact = _oracles(inp, w_bit, asym, dt, None)
     assert_close_to_oracles(to_np_f32(y), y_ref, y_exact, dt, f"b{w_bit} g{group} {dt} asym={asym}")
 
 
-@pytest.mark.parametrize("M", [1, 3, 5, 8, 17, 33])
-def test_row_counts(M):
+@pytest.mark.parametrize("M", [1, 3, 5, 8, 9, 17, 31, 33, 70])
+@pytest.mark.parametrize("path", ["gemv", "mma"])
+def test_row_counts(M, path):
     inp = make_mpq_inputs(1024, 512, 4, 128, "f16", False, M=M, seed=M, device="cuda")
-    y = _run(inp, 4, False)
+    y = _run(inp, 4, False, path)
     y_ref, y_exact = _oracles(inp, 4, False, "f16", None)
     assert_close_to_oracles(to_np_f32(y), y_ref, y_exact, "f16", f"M={M}")
 
@@ -109,9 +124,11 @@ def test_split_k_is_deterministic_and_tickets_reset():
     lib = _cabi.lib()
     try:
         outs = []
-        for L, warps, splitk in ((8, 8, 1), (8, 8, 4), (32, 4, 8), (16, 16, 2), (8, 4, 16)):
+        for L, warps, splitk, path in ((8, 8, 1, "gemv"), (8, 8, 4, "gemv"), (32, 4, 8, "gemv"), (16, 16, 2, "gemv"),
+                                       (8, 4, 16, "gemv"), (8, 4, 1, "mma"), (8, 8, 2, "mma"), (8, 2, 8, "mma"),
+                                       (8, 1, 16, "mma")):
             assert lib.b200bit_set_gemv_tuning(L, warps, splitk) == 0
-            ys = [_run(inp, 4, False) for _ in range(3)]
+            ys = [_run(inp, 4, False, path) for _ in range(3)]
             assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])
             outs.append(ys[0])
         y_ref, y_exact = _oracles(inp, 4, False, "f16", None)
