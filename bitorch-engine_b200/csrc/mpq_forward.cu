@@ -5,6 +5,7 @@
 // (bitorch_engine/layers/qlinear/nbit/cuda/q_linear_cuda.cpp:258-270, mpq_linear_cuda_kernel.cu:603-626, 482-577).
 #include "mpq_gemv.cuh"
 #include "mpq_mma.cuh"
+#include "mpq_stream.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -39,10 +40,12 @@ int sm_count() {
 
 // process-wide tuning override for sweeps (0 = heuristic); set through b200bit_set_gemv_tuning()
 static int g_tune_L = 0, g_tune_warps = 0, g_tune_splitk = 0;
-// 0 = auto, 1 = CUDA-core FHFMA GEMV, 2 = mma.sync small-batch kernel, 3 = general fallback
+// 0 = auto, 1 = CUDA-core FHFMA GEMV, 2 = mma.sync small-batch kernel, 3 = general fallback,
+// 4 = TMA-streamed small-batch kernel
 static int g_path = 0;
 // in auto mode, does M == 1 go to the tensor kernel (1) or stay on the CUDA-core GEMV (0)?
 static int g_mma_for_m1 = 0;
+static unsigned long long* g_trace = nullptr;   // diagnostics: per-warp globaltimer stamps of the stream kernel
 
 // ---------------------------------------------------------------------------------------------------------------
 // General fallback: any g_idx (act-order), any dtype incl. f32, any N / group size.  One thread per column,
@@ -290,6 +293,121 @@ static int launch_mma(const MmaParams& p, const MmaLaunch& l, int w_bit) {
     return set_error(B200BIT_ERR_UNSUPPORTED, "mma: w_bit=%d", w_bit);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-streamed small-batch kernel: plan + tensor maps
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+
+static int make_map_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                       uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+    EncodeTiledFn fn = get_encode_fn();
+    B200_REQUIRE(fn != nullptr, B200BIT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(rc == CUDA_SUCCESS, B200BIT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(rc));
+    return B200BIT_OK;
+}
+
+struct StreamPlan {
+    bool ok;
+    int FJ, warps, grid, S, ngr, rpr, rpr_shift, rps, strips, xs, maxseg;
+    size_t smem;
+};
+
+static StreamPlan plan_stream(int M, int K, int N, int G, int w_bit, int asym, int dtype, bool trivial_gidx) {
+    StreamPlan pl{};
+    pl.ok = false;
+    if (!trivial_gidx || dtype != B200BIT_F16) return pl;
+    if (w_bit != 2 && w_bit != 4 && w_bit != 8) return pl;
+    const int nb = 32 / w_bit;
+    if (N % 32 != 0 || K % (nb * ST_RUN_ROWS) != 0 || K % G != 0) return pl;
+    if (asym && (w_bit == 2 || N % (4 * nb) != 0)) return pl;
+    const int gs = K / G;
+    if (gs % nb != 0) return pl;
+    const int rpg = gs / nb;
+    if (rpg == 8 || rpg == 16) {
+        pl.FJ = rpg / 4; pl.ngr = 32 / rpg; pl.rpr = 1; pl.rpr_shift = 0;
+    } else if (rpg % 32 == 0) {
+        pl.FJ = 8; pl.ngr = 1; pl.rpr = rpg / 32; pl.rpr_shift = -1;
+        for (int sh = 0; sh < 30; ++sh) if ((1 << sh) == pl.rpr) pl.rpr_shift = sh;
+    } else {
+        return pl;
+    }
+    pl.strips = N / 32;
+    pl.rps = (K / nb) / ST_RUN_ROWS;
+    const int cps = g_tune_splitk > 0 ? g_tune_splitk : 1;       // CTAs per SM (sweep hook)
+    int grid = sm_count() * cps;
+    if (grid > pl.strips) grid = pl.strips;
+    pl.grid = grid;
+    const int strips_max = (pl.strips + grid - 1) / grid;          // strips of the busiest CTA
+    const long long rc_ll = (long long)strips_max * pl.rps;
+    if (rc_ll > (1 << 20)) return pl;
+    const int rc_max = int(rc_ll);
+    const int mm = M < 32 ? M : 32;
+    // decode configuration: x staged in shared memory (M <= 8 and the permuted x image fits), up to 16 consumer warps
+    const size_t xs_bytes = size_t(mm) * (size_t(K) * 2 + 64) + ST_RUN_ROWS * nb * 2 +
+                            size_t(mm) * ((K / nb) / (4 * pl.FJ)) * 4 + 64;
+    pl.xs = (mm <= 8 && xs_bytes <= 72 * 1024 && g_tune_L != 32) ? 1 : 0;
+    const int max_warps = pl.xs ? ST_MAX_WARPS : 8;
+    int warps;
+    if (g_tune_warps) {
+        warps = g_tune_warps;
+    } else {
+        const int rounds = (rc_max + max_warps - 1) / max_warps;
+        warps = (rc_max + rounds - 1) / rounds;
+        if (warps < 4) warps = 4;
+    }
+    if (warps > max_warps) warps = max_warps;
+    if (warps > rc_max) warps = rc_max;
+    for (;; warps = (warps + 1) / 2) {                               // shrink the CTA until it fits in shared memory
+        pl.warps = warps;
+        const int q = (rc_max + warps - 1) / warps;
+        const int segs = (q + pl.rps - 1) / pl.rps + 1;              // strips a warp's run range can touch
+        if (segs > ST_MAXSEG) return pl;
+        pl.maxseg = segs;
+        int depth = 16 / warps;                                     // ring slots per consumer warp
+        if (depth < 1) depth = 1;
+        if (depth > q) depth = q;
+        pl.S = warps * depth;
+        pl.smem = size_t(pl.S) * (ST_TILE_BYTES + ST_SZ_BYTES) + size_t(2 * pl.S) * 8 +
+                  (ST_MAX_WARPS * ST_MAXSEG + ST_MAX_WARPS + 4) * 4 + size_t(warps) * segs * mm * 32 * 4 +
+                  (pl.xs ? xs_bytes : 0) + 1024;
+        if (pl.smem <= 200 * 1024 || warps <= 2) break;
+    }
+    pl.ok = pl.smem <= 200 * 1024;
+    return pl;
+}
+
+static int launch_stream(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tz, const StreamParams& p,
+                         const StreamLaunch& l, int w_bit) {
+    switch (w_bit) {
+        case 2: return launch_stream_family<2>(tw, ts, tz, p, l);
+        case 4: return launch_stream_family<4>(tw, ts, tz, p, l);
+        case 8: return launch_stream_family<8>(tw, ts, tz, p, l);
+    }
+    return set_error(B200BIT_ERR_UNSUPPORTED, "stream: w_bit=%d", w_bit);
+}
+
 }  // namespace b200bit
 
 using namespace b200bit;
@@ -320,16 +438,22 @@ int b200bit_set_gemv_tuning(int L, int warps, int splitk) {
 /* path override for benchmarks/tests: 0 auto, 1 CUDA-core GEMV, 2 small-batch mma kernel, 3 general fallback;
  * mma_for_m1: in auto mode route M == 1 to the mma kernel (1) or to the CUDA-core GEMV (0) */
 int b200bit_set_path(int path, int mma_for_m1) {
-    B200_REQUIRE(path >= 0 && path <= 3, B200BIT_ERR_ARG, "path must be in [0,3]");
+    B200_REQUIRE(path >= 0 && path <= 4, B200BIT_ERR_ARG, "path must be in [0,4]");
     g_path = path;
     g_mma_for_m1 = mma_for_m1 ? 1 : 0;
+    return B200BIT_OK;
+}
+
+/* diagnostics: device buffer of [grid][16][8] u64 receiving globaltimer stamps of the stream kernel (NULL = off) */
+int b200bit_set_trace_buffer(void* buf) {
+    g_trace = reinterpret_cast<unsigned long long*>(buf);
     return B200BIT_OK;
 }
 
 size_t b200bit_mpq_forward_workspace_bytes(int M, int K, int N, int w_bit) {
     (void)K; (void)w_bit;
     const int mm = M < 32 ? M : 32;
-    // tickets | split-K partials (<= 64 splits of [mm, N] f32)
+    // tickets | split-K / shared-strip partials (<= 64 contributions of [mm, N] f32)
     return size_t(B200BIT_WS_TICKET_BYTES) + size_t(64) * mm * N * sizeof(float);
 }
 
@@ -351,7 +475,43 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
     if (M == 0) return B200BIT_OK;
 
     const bool trivial = (g_idx == nullptr);
-    // ---- path selection: small-batch tensor kernel (f16) > CUDA-core GEMV (f16/bf16, M <= 4 per pass) > general ----
+    // ---- path selection: TMA-streamed tensor kernel (f16, M <= 32) > mma.sync kernel > CUDA-core GEMV > general ----
+    // auto: M == 1 -> CUDA-core FHFMA GEMV (fastest measured at batch 1, profiles/r1_*); 2 <= M: TMA-streamed tensor kernel
+    const StreamPlan sp = (g_path == 4 || (g_path == 0 && M >= 2)) ? plan_stream(M, K, N, G, w_bit, asym, dtype, trivial)
+                                                                 : StreamPlan{};
+    if (sp.ok) {
+        B200_REQUIRE(workspace && workspace_bytes >= B200BIT_WS_TICKET_BYTES, B200BIT_ERR_WORKSPACE,
+                     "mpq_forward: workspace (>= %d bytes, zero-initialised head) required", B200BIT_WS_TICKET_BYTES);
+        CUtensorMap tw, ts, tz;
+        int rc = make_map_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_UINT32, qweight, uint64_t(N), uint64_t(K / nb), uint64_t(N) * 4,
+                             32, ST_RUN_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != B200BIT_OK) return rc;
+        rc = make_map_2d(&ts, CU_TENSOR_MAP_DATA_TYPE_UINT16, scales, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
+                         uint32_t(sp.ngr), CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        if (asym)
+            rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT32, zeros, uint64_t(N / nb), uint64_t(G),
+                             uint64_t(N / nb) * 4, uint32_t(32 / nb), uint32_t(sp.ngr), CU_TENSOR_MAP_SWIZZLE_NONE);
+        else
+            rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT16, zeros, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
+                             uint32_t(sp.ngr), CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        for (int m0 = 0; m0 < M; m0 += 32) {
+            const int mc = (M - m0) < 32 ? (M - m0) : 32;
+            StreamParams p{};
+            p.x = reinterpret_cast<const uint16_t*>(x) + size_t(m0) * K;
+            p.y = reinterpret_cast<uint16_t*>(y) + size_t(m0) * N;
+            p.zero_page = reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(workspace) + B200BIT_WS_ZERO_OFFSET);
+            p.M = mc; p.K = K; p.N = N; p.strips = sp.strips; p.rps = sp.rps; p.ngr = sp.ngr; p.rpr = sp.rpr;
+            p.rpr_shift = sp.rpr_shift; p.asym = asym; p.S = sp.S; p.maxseg = sp.maxseg; p.trace = g_trace; p.debug_no_x = (g_tune_L == 16);
+            StreamLaunch l{};
+            l.MT = (mc + 7) / 8; l.FJ = sp.FJ; l.warps = sp.warps; l.grid = sp.grid; l.xs = sp.xs;
+            l.smem = sp.smem; l.flags = flags; l.stream = stream;
+            rc = launch_stream(tw, ts, tz, p, l, w_bit);
+            if (rc != B200BIT_OK) return rc;
+        }
+        return B200BIT_OK;
+    }
     const MmaPlan mp = (g_path == 0 || g_path == 2) ? plan_mma(M, K, N, G, w_bit, asym, dtype, trivial) : MmaPlan{};
     if (mp.ok && !(g_path == 0 && M == 1 && !g_mma_for_m1)) {
         float* part = nullptr;
@@ -361,7 +521,7 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
             const size_t need = size_t(B200BIT_WS_TICKET_BYTES) + size_t(mp.splitk) * mm * N * sizeof(float);
             B200_REQUIRE(workspace && workspace_bytes >= need, B200BIT_ERR_WORKSPACE,
                          "mpq_forward: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
-            B200_REQUIRE(size_t(N / 32) * sizeof(unsigned) <= B200BIT_WS_TICKET_BYTES, B200BIT_ERR_SHAPE,
+            B200_REQUIRE(size_t(N / 32) * sizeof(unsigned) <= B200BIT_WS_ZERO_OFFSET, B200BIT_ERR_SHAPE,
                          "mpq_forward: N=%d too large for the ticket area", N);
             tick = reinterpret_cast<unsigned*>(workspace);
             part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B200BIT_WS_TICKET_BYTES);
@@ -402,7 +562,7 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
         const size_t need = size_t(B200BIT_WS_TICKET_BYTES) + size_t(pl.splitk) * mm * N * sizeof(float);
         B200_REQUIRE(workspace && workspace_bytes >= need, B200BIT_ERR_WORKSPACE,
                      "mpq_forward: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
-        B200_REQUIRE(strips * sizeof(unsigned) <= B200BIT_WS_TICKET_BYTES, B200BIT_ERR_SHAPE,
+        B200_REQUIRE(strips * sizeof(unsigned) <= B200BIT_WS_ZERO_OFFSET, B200BIT_ERR_SHAPE,
                      "mpq_forward: N=%d too large for the ticket area", N);
         tickets = reinterpret_cast<unsigned*>(workspace);
         ws_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B200BIT_WS_TICKET_BYTES);

@@ -18,7 +18,8 @@
  *   - dtype codes: B200BIT_F32 / F16 / BF16 name the activation/scale/output element type (the reference switches on
  *     x.dtype(), mpq_linear_cuda_kernel.cu:517-575).
  *   - workspace: caller-owned scratch, >= the matching *_workspace_bytes() and 16-byte aligned.  Its first
- *     B200BIT_WS_TICKET_BYTES bytes must be zero before the FIRST use; kernels leave them zero again.
+ *     B200BIT_WS_TICKET_BYTES bytes must be zero before the FIRST use; kernels leave them zero again
+ *     (split-K tickets in [0, B200BIT_WS_ZERO_OFFSET), a read-only zero page after it).
  */
 #ifndef B200BIT_H_
 #define B200BIT_H_
@@ -50,6 +51,7 @@ extern "C" {
 #define B200BIT_ERR_CUDA (-5)         /* a CUDA runtime call failed (message has the CUDA string)  */
 
 #define B200BIT_WS_TICKET_BYTES 16384
+#define B200BIT_WS_ZERO_OFFSET 12288   /* [12288, 16384) of the head is a page the kernels only ever read as zeros */
 
 /* flags for the `flags` argument of the forward entry points */
 #define B200BIT_FLAG_PDL 1u           /* launch with programmatic dependent launch (graph/stream overlap) */
@@ -81,6 +83,10 @@ B200BIT_API int b200bit_set_gemv_tuning(int lanes_per_row, int warps, int splitk
 /* Kernel-path override (process-wide): 0 auto, 1 CUDA-core FHFMA GEMV, 2 small-batch mma.sync kernel, 3 general
  * fallback; mma_for_m1 selects, in auto mode, whether M == 1 uses the tensor kernel (1) or the CUDA-core GEMV (0). */
 B200BIT_API int b200bit_set_path(int path, int mma_for_m1);
+/* Diagnostics: device buffer of [grid][16][8] uint64 that receives %globaltimer stamps from the TMA-streamed kernel
+ * (per CTA, per warp: start, init done, dependency wait done, first tile landed, first run done, all runs done,
+ * CTA barrier passed, end); NULL switches tracing off. */
+B200BIT_API int b200bit_set_trace_buffer(void* device_buffer);
 
 #ifdef __cplusplus
 }

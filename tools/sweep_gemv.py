@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--configs", default="0:0:0,8:8:1,8:8:2,8:8:4,8:4:1,8:4:2,8:4:4,8:16:1,8:16:2,16:8:2,16:8:4,"
                                          "16:4:4,32:8:4,32:8:8,32:4:8,16:16:2,8:2:4,8:2:8")
     ap.add_argument("--pdl", default="0,1")
-    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 CUDA-core gemv, 2 mma small-batch")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 CUDA-core gemv, 2 mma small-batch, 4 TMA stream")
     ap.add_argument("--reps", type=int, default=20)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
