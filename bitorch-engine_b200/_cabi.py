@@ -9,7 +9,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200bit.so")
 
-F32, F16, BF16 = 0, 1, 2
+F32, F16, BF16, I8, I32 = 0, 1, 2, 3, 4
 FLAG_PDL = 1
 WS_TICKET_BYTES = 16384
 
@@ -27,6 +27,15 @@ PROTOTYPES = {
     "b200bit_mpq_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                      _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                      _c_void_p, _c_size_t, _c_uint, _c_void_p]),
+    "b200bit_mpq_grad_input": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p]),
+    "b200bit_mpq_dequant": (_c_int, [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p, _c_void_p]),
+    "b200bit_exl2_dequant": (_c_int, [_c_void_p] * 6 + [_c_int, _c_int, ctypes.POINTER(_c_int), _c_void_p]),
+    "b200bit_mpq_pack_weight": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p]),
+    "b200bit_diodemix_mpq_step": (_c_int, [_c_void_p] * 6 + [_c_int] * 8 + [ctypes.c_double] * 4 + [_c_int, _c_void_p]),
+    "b200bit_diodemix_binary_step": (_c_int, [_c_void_p] * 5 + [_c_size_t, _c_int] + [ctypes.c_double] * 3 + [_c_void_p]),
+    "b200bit_binary_pack": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_void_p]),
+    "b200bit_binary_relayout": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "b200bit_binary_gemm": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
 }
 
 _lib = None
@@ -77,6 +86,10 @@ def dtype_code(dtype):
         return BF16
     if dtype == torch.float32:
         return F32
+    if dtype == torch.int8:
+        return I8
+    if dtype == torch.int32:
+        return I32
     raise NotImplementedError(f"b200bit: tensor type not supported: {dtype}")
 
 

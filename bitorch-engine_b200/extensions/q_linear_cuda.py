@@ -69,3 +69,184 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
             ws.data_ptr(), ws.numel(), _cabi.FLAG_PDL if pdl else 0, stream)
     _cabi.check(rc)
     return y
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def mpq_grad_input(qweight, scales, zeros, g_idx, output_gradient, a_bit, w_bit, asym):
+    """dx[M,K] = dy[M,N] @ dequant(qweight)^T  (q_linear_cuda.cpp:272-284 -> mpq_linear_cuda_kernel.cu:1198-1223)."""
+    _check_cuda(output_gradient, "output_gradient")
+    _check_cuda(qweight, "qweight")
+    if a_bit != 16:
+        raise NotImplementedError(f"a_bit:{a_bit} has not been supported yet!")
+    dy = output_gradient.contiguous()
+    M, N = dy.shape
+    K = qweight.shape[0] * 32 // w_bit
+    G = scales.shape[0]
+    if scales.dtype != dy.dtype:
+        raise ValueError(f"scales dtype {scales.dtype} must match output_gradient dtype {dy.dtype}")
+    trivial = _gidx_is_trivial(g_idx, K, G)
+    dx = torch.empty((M, K), dtype=dy.dtype, device=dy.device)
+    if M == 0:
+        return dx
+    with torch.cuda.device(dy.device):
+        rc = _cabi.lib().b200bit_mpq_grad_input(
+            dy.data_ptr(), qweight.contiguous().data_ptr(), scales.contiguous().data_ptr(), zeros.contiguous().data_ptr(),
+            None if trivial else g_idx.contiguous().data_ptr(), dx.data_ptr(), M, K, N, G, w_bit, int(bool(asym)),
+            _cabi.dtype_code(dy.dtype), torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc)
+    return dx
+
+
+def mpq_dequant(qweight, scales, zeros, g_idx, w_bit, asym, fused=False, perm=None):
+    """fp weight [K,N] in scales.dtype, bit-identical to the reference's Python unpack_qweight (layer_type 1).
+    Not part of the reference extension (it does this with ~6 torch kernels, utils.py:31-51); exposed here because the
+    host-side unpack_qweight / M>32 forward / MBWQ backward call it."""
+    _check_cuda(qweight, "qweight")
+    K = qweight.shape[0] * 32 // w_bit
+    N = qweight.shape[1]
+    G = scales.shape[0]
+    trivial = _gidx_is_trivial(g_idx, K, G)
+    out = torch.empty((K, N), dtype=scales.dtype, device=qweight.device)
+    with torch.cuda.device(qweight.device):
+        rc = _cabi.lib().b200bit_mpq_dequant(
+            qweight.contiguous().data_ptr(), scales.contiguous().data_ptr(), zeros.contiguous().data_ptr(),
+            None if trivial else g_idx.contiguous().data_ptr(), out.data_ptr(), K, N, G, w_bit, int(bool(asym)),
+            _cabi.dtype_code(scales.dtype), int(bool(fused)), _ptr(None if perm is None else perm.contiguous()),
+            torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc)
+    return out
+
+
+def mpq_pack_weight(weight, scales, zeros, g_idx, w_bit, asym, zeros_unpacked=False, perm=None):
+    """int32 [K*w_bit/32, N] from fp weight [K,N], bit-identical to the reference's pack_fp_weight (utils.py:72-147)."""
+    _check_cuda(weight, "weight")
+    K, N = weight.shape
+    G = scales.shape[0]
+    weight = weight.to(scales.dtype).contiguous()
+    zeros = zeros.contiguous()
+    if asym and zeros_unpacked:
+        zeros = zeros.to(scales.dtype).contiguous()
+    trivial = _gidx_is_trivial(g_idx, K, G)
+    out = torch.empty((K * w_bit // 32, N), dtype=torch.int32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        rc = _cabi.lib().b200bit_mpq_pack_weight(
+            weight.data_ptr(), scales.contiguous().data_ptr(), zeros.data_ptr(),
+            None if trivial else g_idx.contiguous().data_ptr(), _ptr(None if perm is None else perm.contiguous()),
+            out.data_ptr(), K, N, G, w_bit, int(bool(asym)), int(bool(zeros_unpacked)), _cabi.dtype_code(scales.dtype),
+            torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc)
+    return out
+
+
+def unpack_zeros(qzeros, w_bit):
+    """packed int32 [G, N*w_bit/32] -> integer zero points [G, N] including the +1 (utils.py:36-41).  [G,N] is
+    K/group times smaller than the weight: plain torch ops."""
+    nb = 32 // w_bit
+    shifts = torch.arange(0, 32, w_bit, dtype=torch.int32, device=qzeros.device).view(1, 1, nb)
+    z = (qzeros.unsqueeze(2) >> shifts) & ((1 << w_bit) - 1)
+    return (z + 1).reshape(qzeros.shape[0], -1)
+
+
+def pack_zeros(zeros, w_bit):
+    """integer(-valued) zero points [G, N] -> packed int32 [G, N*w_bit/32]: trunc, (z-1) & mask, LSB first along N
+    (gptq_style_zeros_packing, quant_operators.py:348-368)."""
+    nb = 32 // w_bit
+    G, N = zeros.shape
+    z = (zeros.reshape(G, N // nb, nb).to(torch.int32) - 1) & ((1 << w_bit) - 1)
+    shifts = torch.arange(0, 32, w_bit, dtype=torch.int32, device=zeros.device).view(1, 1, nb)
+    return (z << shifts).sum(dim=-1).to(torch.int32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MBWQ ("Q4" GPTQ-style and exl2 mixed-bit) entry points (q_linear_cuda.cpp:286-354)
+# ---------------------------------------------------------------------------------------------------------------
+def _perm_is_identity(q_perm, K):
+    """q_perm == 0 everywhere is the reference's "no permutation" marker (mbwq_linear_cuda_kernel.cu:777 evaluates
+    torch::all(q_perm == 0).item() on EVERY call -- a device sync); arange(K) is the same map.  Verdict cached on the
+    tensor object / version."""
+    if q_perm is None:
+        return True
+    tag = getattr(q_perm, "_b200bit_identity", None)
+    if tag is not None and tag[0] == q_perm._version:
+        return tag[1]
+    ident = bool(torch.all(q_perm == 0).item()) or bool(
+        torch.equal(q_perm.to(torch.int64) & 0xFFFF, torch.arange(K, device=q_perm.device)))
+    q_perm._b200bit_identity = (q_perm._version, ident)
+    return ident
+
+
+def mbwq_trans_qweight(qweight, q_groups, use_mbw, height, groups, bits):
+    """(qweight, rows) -- q_linear_cuda.cpp:286-296 -> mbwq_linear_trans_qweight_cuda (:536-626).  The in-place
+    "shuffle" of the reference is compiled to a no-op (exl2/config.h:16-21, all QMODE_* = 0), so qweight is returned
+    untouched; rows = cumulative weight-row counts per bit-width (8,6,5,4,3,2) + the bit-width mask, [] for use_mbw=False."""
+    _check_cuda(qweight, "qweight")
+    if not use_mbw:
+        if bits not in (2, 4):
+            raise NotImplementedError(f"Error: weight bit width:{bits} has not been supported yet!")
+        return qweight, []
+    qg = q_groups.detach().to("cpu").to(torch.int64).view(-1)[: 2 * groups] & 0xFFFF     # one D2H copy, as :562
+    counts = {8: 0, 6: 0, 5: 0, 4: 0, 3: 0, 2: 0}
+    mask, row = 0, 0
+    for i in range(groups):
+        b = int(qg[2 * i])
+        if b not in counts:
+            raise NotImplementedError(f"Error: weight bit width:{b} has not been supported yet!")
+        mask |= 1 << (b - 1)
+        rows = (int(qg[2 * i + 3]) - int(qg[2 * i + 1])) * 32 // b if i < groups - 1 else height - row
+        counts[b] += rows
+        row += rows
+    out, acc = [], 0
+    for b in (8, 6, 5, 4, 3, 2):
+        acc += counts[b]
+        out.append(acc)
+    return qweight, out + [mask]
+
+
+def mbwq_q42fp_weight(qweight, scales, zeros, group_size, bits, q_perm):
+    """fp16 weight [K,N] of a GPTQ-style 4/2-bit matrix, rows scattered through q_perm (q_linear_cuda.cpp:298-308)."""
+    _check_cuda(qweight, "qweight")
+    if scales.dtype != torch.float16:
+        raise TypeError("mbwq_q42fp_weight: scales must be torch.half")
+    K = qweight.shape[0] * 32 // bits
+    perm = None if _perm_is_identity(q_perm, K) else q_perm
+    return mpq_dequant(qweight, scales, zeros, None, bits, False, fused=True, perm=perm)
+
+
+def mbwq_q4_forward(x, qweight, scales, zeros, group_size, q_perm, bits):
+    """y = x[:, q_perm] @ W  (q_linear_cuda.cpp:310-321 -> mbwq_linear_q4_forward_cuda :742-825).  Same packed layout as
+    MPQ-sym with contiguous groups, so it runs on the same kernels; the activation gather is one index_select."""
+    _check_cuda(x, "x")
+    if x.dtype != torch.float16:
+        raise TypeError("mbwq_q4_forward: x must be torch.half")          # TORCH_CHECK at :753-754
+    K = x.shape[1]
+    if not _perm_is_identity(q_perm, K):
+        x = x.index_select(1, q_perm.to(torch.int64) & 0xFFFF)
+    return mpq_forward(x, qweight, scales, zeros, None, 16, bits, False)
+
+
+def mbwq_exl2fp_weight(qweight, scales, zeros, q_perm, q_group_map, rows):
+    """fp16 weight [K,N] of an exl2 mixed-bit matrix (q_linear_cuda.cpp:323-336 -> :849-897)."""
+    _check_cuda(qweight, "qweight")
+    import ctypes
+    K, N = q_group_map.numel() // 2, qweight.shape[1]
+    out = torch.empty((K, N), dtype=torch.float16, device=qweight.device)
+    rows6 = (ctypes.c_int * 6)(*[int(r) for r in rows[:6]])
+    perm = None if (q_perm is None or _perm_is_identity(q_perm, K)) else q_perm.contiguous()
+    with torch.cuda.device(qweight.device):
+        rc = _cabi.lib().b200bit_exl2_dequant(qweight.contiguous().data_ptr(), scales.contiguous().data_ptr(),
+                                              zeros.contiguous().data_ptr(), _ptr(perm),
+                                              q_group_map.contiguous().data_ptr(), out.data_ptr(), K, N, rows6,
+                                              torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc)
+    return out
+
+
+def mbwq_exl2_forward(x, qweight, scales, zeros, q_perm, q_group_map, rows, use_cublas=False):
+    """y = x @ W_exl2 (q_linear_cuda.cpp:338-354 -> :926-1007).  Round 1: dequantise (one kernel) + cuBLAS for every M --
+    the path the reference itself takes above 32 rows (:947-957); a fused mixed-bit GEMV is listed in DESIGN.md "next"."""
+    _check_cuda(x, "x")
+    W = mbwq_exl2fp_weight(qweight, scales, zeros, q_perm, q_group_map, rows)
+    return torch.matmul(x, W)

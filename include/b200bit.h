@@ -42,6 +42,8 @@ extern "C" {
 #define B200BIT_F32 0
 #define B200BIT_F16 1
 #define B200BIT_BF16 2
+#define B200BIT_I8 3    /* binary path: int8 +-1 weights */
+#define B200BIT_I32 4   /* binary path: raw integer output */
 
 #define B200BIT_OK 0
 #define B200BIT_ERR_ARG (-1)          /* null pointer / bad enum                                   */
@@ -76,6 +78,83 @@ B200BIT_API size_t b200bit_mpq_forward_workspace_bytes(int M, int K, int N, int 
 B200BIT_API int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scales, const void* zeros,
                         const int32_t* g_idx, void* y, int M, int K, int N, int G, int w_bit, int asym, int dtype,
                         void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * MPQ grad_input:  dx[M,K] = dy[M,N] @ W^T  (same dequantisation as the forward; fp32 accumulation; deterministic).
+ * Replaces q_linear_cuda.mpq_grad_input (q_linear_cuda.cpp:272-284 -> mpq_linear_cuda_kernel.cu:1198-1223,
+ * back_quant_mm_kernel{,_asym} :635-1049).  Argument meaning as b200bit_mpq_forward.
+ * ------------------------------------------------------------------------------------------------------------ */
+B200BIT_API int b200bit_mpq_grad_input(const void* dy, const int32_t* qweight, const void* scales, const void* zeros,
+                                       const int32_t* g_idx, void* dx, int M, int K, int N, int G, int w_bit, int asym,
+                                       int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dequantise the whole weight to out[K,N] in `dtype`, bit-identical to the reference's Python unpack_qweight
+ * (layer_type 1; bitorch_engine/layers/qlinear/nbit/cuda/utils.py:5-69): sym rnd(rnd(q*s) - z), asym rnd(s*(q - zq)),
+ * every op rounded to dtype.  One pass, no temporaries (the reference materialises int32 [K/nb,nb,N] and int8 [K,N]).
+ * ------------------------------------------------------------------------------------------------------------ */
+B200BIT_API int b200bit_mpq_dequant(const int32_t* qweight, const void* scales, const void* zeros, const int32_t* g_idx,
+                                    void* out, int K, int N, int G, int w_bit, int asym, int dtype, int fused,
+                                    const int16_t* perm, void* stream);
+/* `fused` = 1 selects the rounding of the reference's CUDA dequant kernels, rnd(fma(s, q, -z)) (mbwq_q42fp_weight ->
+ * reconstruct_q{4,2}_gptq_kernel, mbwq_linear_cuda_kernel.cu:314-501); `perm` (int16 [K], nullable) scatters packed row
+ * k to output row perm[k] (MBWQ q_perm, :398-399).
+ *
+ * exl2 mixed bit-width dequantise (mbwq_exl2fp_weight -> reconstruct_exl2_kernel, :92-308): rows6 = the six
+ * cumulative section ends (8,6,5,4,3,2 bit) returned by mbwq_trans_qweight, a HOST array; fp16 only. */
+B200BIT_API int b200bit_exl2_dequant(const int32_t* qweight, const void* scales, const void* zeros, const int16_t* perm,
+                                     const int16_t* q_group_map, void* out, int K, int N, const int* rows6_host,
+                                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Quantise + bit-pack weight[K,N] (dtype) into qweight_out int32 [K*w_bit/32, N], bit-identical to the reference's
+ * pack_fp_weight (utils.py:72-147): sym clamp(rint(rnd(rnd(w+z)/s))), asym clamp(rint(rnd(rnd(w/s)+zq))).
+ * zeros: sym dtype [G,N]; asym packed int32 [G,N*w_bit/32] (zeros_unpacked=0) or integer zero points stored as dtype
+ * [G,N] (zeros_unpacked=1: the `unpacked_zeros` argument).  perm: optional int16 [K] row gather (MBWQ q_perm).
+ * ------------------------------------------------------------------------------------------------------------ */
+B200BIT_API int b200bit_mpq_pack_weight(const void* weight, const void* scales, const void* zeros, const int32_t* g_idx,
+                                        const int16_t* perm, int32_t* qweight_out, int K, int N, int G, int w_bit,
+                                        int asym, int zeros_unpacked, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused DiodeMix update of an MPQ weight (one kernel): unpack -> Adam moments -> normalised gradient -> step ->
+ * (update_zeros: the every-5th-step zero-point update) -> re-quantise + re-pack.  Replaces the MPQWeightParameter
+ * branch of qweight_update_fn (bitorch_engine/utils/model_helper.py:485-530, update_zeros :330-360,
+ * gptq_style_unpacking / gptq_style_zeros_packing quant_operators.py:310-368, pack_fp_weight utils.py:72-147),
+ * ~25 torch kernels.  Contiguous groups only (g_idx == arange(K) // group).  storage_dtype: dtype of scales (and of
+ * sym zeros); compute_dtype: optimizer dtype of exp_avg_l / exp_avg_s (f32 or == storage); grad_dtype: storage or
+ * compute dtype.  step_size already carries the bias correction (model_helper.py:501-506).
+ * ------------------------------------------------------------------------------------------------------------ */
+B200BIT_API int b200bit_diodemix_mpq_step(int32_t* qweight, const void* scales, void* zeros, const void* grad,
+                                          void* exp_avg_l, void* exp_avg_s, int K, int N, int G, int w_bit, int asym,
+                                          int storage_dtype, int compute_dtype, int grad_dtype, double beta1, double beta2,
+                                          double eps, double step_size, int update_zeros, void* stream);
+
+/* Fused DiodeMix update of a binary (int8 +-1) weight: two lerps, sign descent, conditional flip.  Replaces the
+ * BinaryLinearParameter branch of qweight_update_fn (model_helper.py:437-445).  Exactly one of grad_i8 / grad_c
+ * (compute dtype) is non-NULL. */
+B200BIT_API int b200bit_diodemix_binary_step(int8_t* weight, const int8_t* grad_i8, const void* grad_c, void* exp_avg_l,
+                                             void* exp_avg_s, size_t numel, int compute_dtype, double beta1, double beta2,
+                                             double lr, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Binary (1-bit) Linear:  y[m,n] = K - 2*popc(bits(x[m,:]) xor bits(w[n,:])),  sign bit = (v >= 0); integer-exact.
+ * Replaces binary_linear_cuda.{forward, w_pack, mm} (binary_linear_cuda.cpp:92-122; kernels
+ * binary_linear_cuda_kernel.cu:59-394, host flows :481-626, :830-889) without the per-call cudaMalloc/cudaFree.
+ *   canonical bit matrix: [rows][stride_bytes] bytes, byte kb holds k = 8*kb..8*kb+7, bit (7 - k%8), zero padded,
+ *                         stride_bytes a multiple of 4 with stride_bytes*8 >= K.
+ *   b200bit_binary_pack     : float/half/bf16/int8 matrix -> canonical bits.  transposed_input = 0: in is [rows, K];
+ *                             1: in is [K, rows] (the reference's weight.t().contiguous() / mm operand y).
+ *   b200bit_binary_relayout : canonical <-> the reference's packed uint8 weight streams; layout 2 = BTC
+ *                             (k%128==0, n%8==0; :118 + :22-41), 1 = BSTC (k%32==0, n%32==0; :201 + :22-41).
+ *   b200bit_binary_gemm     : canonical x bits [M] and w bits [N] -> out [M,N] in out_dtype (F32/F16/BF16/I32).
+ * ------------------------------------------------------------------------------------------------------------ */
+B200BIT_API int b200bit_binary_pack(const void* in, int in_dtype, int rows, int K, int transposed_input, uint8_t* out,
+                                    int stride_bytes, void* stream);
+B200BIT_API int b200bit_binary_relayout(const uint8_t* in, uint8_t* out, int N, int K, int layout, int to_reference,
+                                        int canon_stride_bytes, void* stream);
+B200BIT_API int b200bit_binary_gemm(const uint8_t* x_bits, const uint8_t* w_bits, void* out, int M, int N, int K,
+                                    int stride_bytes, int out_dtype, void* stream);
 
 /* Sweep hook for bench.py / tests (process-wide; 0 = built-in heuristic): lanes per packed-row segment (8, 16, 32),
  * warps per CTA (1..16), split-K factor of the decode GEMV.  No reference counterpart. */

@@ -108,6 +108,108 @@ def gen_nbit():
     print(f"nbit: {len(cases)} cases -> tests/golden/nbit_cases.npz")
 
 
+def gen_optim():
+    """DiodeMix weight updates by the reference's own qweight_update_fn (utils/model_helper.py:363-530), CPU."""
+    from bitorch_engine.layers.qlinear.nbit import MPQWeightParameter
+    from bitorch_engine.layers.qlinear.binary import BinaryLinearParameter
+    from bitorch_engine.utils.model_helper import qweight_update_fn
+    from bitorch_engine.utils.quant_operators import nv_tensor_quant
+
+    out, cases = {}, []
+    K, N = 256, 64
+    cid = 0
+    for w_bit, group in ((4, 128), (2, 32), (8, 64)):
+        for odt in ("f32", "f16"):
+            seed = 5000 + cid
+            qweight, scales, zeros, g_idx, _, _ = make_inputs(K, N, w_bit, group, "f16", True, False, seed)
+            qp = MPQWeightParameter(qweight.clone(), requires_grad=False, scales=scales, zeros=zeros.clone(), g_idx=g_idx,
+                                    w_bit=w_bit, asym=True, group_size=group, layer_type=1)
+            tdt = TORCH_DT[odt]
+            m = torch.zeros((K, N), dtype=tdt)
+            v = torch.zeros((K, N), dtype=tdt)
+            step = torch.zeros(1)
+            gen = torch.Generator().manual_seed(seed + 1)
+            name = f"o{cid}"
+            out[f"{name}_qweight0"] = qweight.numpy()
+            out[f"{name}_scales"] = _bits(scales)
+            out[f"{name}_zeros0"] = zeros.numpy()
+            for it in range(1, 7):
+                grad = (torch.randn((K, N), generator=gen) * 0.05).half()
+                out[f"{name}_grad{it}"] = _bits(grad)
+                qweight_update_fn(qweight=qp, exp_avg_s=v, exp_avg_l=m, step=step, lr=2e-3, weight_decay=0.0, beta1=0.99,
+                                  beta2=0.9999, eps=1e-6, dtype=tdt, correct_bias=True, projector=None, grad=grad)
+                out[f"{name}_qweight{it}"] = qp.data.numpy().copy()
+                out[f"{name}_zeros{it}"] = qp.zeros.numpy().copy()
+                out[f"{name}_m{it}"] = _bits(m) if odt != "f32" else m.numpy().copy()
+                out[f"{name}_v{it}"] = _bits(v) if odt != "f32" else v.numpy().copy()
+            cases.append((name, "mpq", w_bit, group, odt, K, N))
+            cid += 1
+    # binary branch
+    for odt in ("f32", "f16"):
+        gen = torch.Generator().manual_seed(7000 + cid)
+        rows, cols = 64, 128
+        w = torch.where(torch.rand((rows, cols), generator=gen) < 0.5, -1, 1).to(torch.int8)
+        bp = BinaryLinearParameter(w.clone(), requires_grad=False)
+        tdt = TORCH_DT[odt]
+        m = torch.zeros((rows, cols), dtype=tdt)
+        v = -(w.clone().sign().to(tdt) * (torch.rand((rows, cols), generator=gen).to(tdt) * 1e-3))
+        step = torch.zeros(1)
+        name = f"o{cid}"
+        out[f"{name}_w0"] = w.numpy()
+        out[f"{name}_v0"] = _bits(v) if odt != "f32" else v.numpy().copy()
+        for it in range(1, 5):
+            g = nv_tensor_quant(torch.randn((rows, cols), generator=gen))[0].to(torch.int8)
+            out[f"{name}_grad{it}"] = g.numpy()
+            bp.grad = None
+            # the reference reads qweight.grad (integer grads need GreenBit's torch); hand it over the same way
+            object.__setattr__(bp, "_grad_holder", g)
+            type(bp).grad = property(lambda self: self._grad_holder)
+            qweight_update_fn(qweight=bp, exp_avg_s=v, exp_avg_l=m, step=step, lr=1e-3, beta1=0.99, beta2=0.9999,
+                              dtype=tdt)
+            del type(bp).grad
+            out[f"{name}_w{it}"] = bp.data.numpy().copy()
+            out[f"{name}_m{it}"] = _bits(m) if odt != "f32" else m.numpy().copy()
+            out[f"{name}_v{it}"] = _bits(v) if odt != "f32" else v.numpy().copy()
+        cases.append((name, "binary", 1, 0, odt, rows, cols))
+        cid += 1
+    out["cases"] = np.array([",".join(map(str, c)) for c in cases])
+    np.savez_compressed(os.path.join(GOLD, "optim_cases.npz"), **out)
+    print(f"optim: {len(cases)} cases -> tests/golden/optim_cases.npz")
+
+
+def gen_layers():
+    """state_dict layout of the reference MPQLinearCuda before / after prepare_params, and the double-dequantised
+    scales / zeros it produces (mpq_layer.py:163-204) for random statistics."""
+    import json
+    from bitorch_engine.layers.qlinear.nbit.cuda import MPQLinearCuda
+    specs, tensors = [], {}
+    configs = [dict(w_bit=4, group_size=128, dq_group_size=256), dict(w_bit=2, group_size=32, dq_group_size=32),
+               dict(w_bit=4, group_size=128, use_gba_quant=False), dict(w_bit=4, group_size=64, dq_group_size=64, asym=True),
+               dict(w_bit=2, group_size=32, dq_group_size=32, asym=True, dq_mode=1), dict(w_bit=8, group_size=256),
+               dict(w_bit=1, group_size=128, dq_group_size=128)]
+    for ci, kw in enumerate(configs):
+        layer = MPQLinearCuda(256, 512, requires_grad=False, **kw)
+        before = {k: [list(v.shape), str(v.dtype)] for k, v in layer.state_dict().items()}
+        g = torch.Generator().manual_seed(9000 + ci)
+        for name, buf in layer.named_buffers():
+            if buf.dtype == torch.uint8:
+                buf.copy_(torch.randint(0, 256, buf.shape, dtype=torch.uint8, generator=g))
+            elif buf.is_floating_point() and name not in ("bias",):
+                buf.copy_((torch.rand(buf.shape, generator=g) * 0.02 + 0.001).to(buf.dtype))
+            if name in ("qstatistic", "qscales", "qscales_zeros", "qscales_scales", "qzeros_zeros", "qzeros_scales"):
+                tensors[f"l{ci}_{name}"] = _bits(buf) if buf.dtype in (torch.float16, torch.bfloat16) else buf.numpy().copy()
+        layer.prepare_params()
+        after = {k: [list(v.shape), str(v.dtype)] for k, v in layer.state_dict().items()}
+        tensors[f"l{ci}_scales_out"] = _bits(layer.scales)
+        if layer.zeros.dtype != torch.int32:
+            tensors[f"l{ci}_zeros_out"] = _bits(layer.zeros)
+        specs.append(dict(kwargs=kw, before=before, after=after))
+    with open(os.path.join(GOLD, "layer_specs.json"), "w") as fh:
+        json.dump(specs, fh, indent=1, sort_keys=True)
+    np.savez_compressed(os.path.join(GOLD, "layer_prepare.npz"), **tensors)
+    print(f"layers: {len(specs)} configs -> tests/golden/layer_specs.json, layer_prepare.npz")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["nbit"]
     for w in what:

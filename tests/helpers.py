@@ -95,3 +95,43 @@ def assert_close_to_oracles(y, y_ref, y_exact, dt, what=""):
     worst = float(np.max(np.abs(y - y_exact) - bound))
     assert worst <= 0, f"{what}: element-wise error exceeds {ELEM_RTOL[dt]}*|y| + 1e-4*rms by {worst:.3e}"
     return nrm
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# exl2 mixed-bit fixtures: restatement of the format helpers in the reference's tests
+# (tests/layers/util.py:31-93 get_packed_info / get_q_groups), strategy of test_nbit_linear_mixbits.py:26-29
+# ---------------------------------------------------------------------------------------------------------------
+def exl2_packed_info(channels, n_bits, bits_prop, group_size):
+    groups = rows = 0
+    used = []
+    sizes = list(group_size.values())
+    for i in range(len(bits_prop)):
+        gs = sizes[i]
+        ch = max(1, int(channels * bits_prop[i]) // gs) * gs if i < len(bits_prop) - 1 else channels - sum(used)
+        used.append(ch)
+        groups += ch // gs
+        rows += ch // 32 * n_bits[i]
+    return groups, rows
+
+
+def exl2_q_groups(groups, n_bits, group_size, channels, bits_prop):
+    import math
+    ends = []
+    sizes = list(group_size.values())
+    for i in range(len(bits_prop)):
+        if i < len(bits_prop) - 1:
+            e = max(1, int(channels * bits_prop[i]) // sizes[i]) * sizes[i] + (ends[-1] if ends else 0)
+        else:
+            e = channels
+        ends.append(e)
+    q = []
+    for i, bits in enumerate(n_bits):
+        rows = ends[i] - (ends[i - 1] if i else 0)
+        q += [bits, 0] * (rows // group_size[str(bits)])
+    out_row, rem = 0, channels
+    for g in range(groups):
+        bits = q[2 * g]
+        gs = group_size[str(bits)]
+        q[2 * g + 1] = out_row
+        out_row += math.ceil(min(gs, rem) / (32 / bits))
+    return q
