@@ -33,8 +33,8 @@ TORCH_DT = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}
 def _bits(t):
     """torch half/bf16 -> uint16 numpy bits; float32 -> float32 numpy."""
     if t.dtype in (torch.float16, torch.bfloat16):
-        return t.contiguous().view(torch.int16).numpy().view(np.uint16)
-    return t.contiguous().numpy()
+        return t.contiguous().view(torch.int16).numpy().view(np.uint16).copy()
+    return t.contiguous().numpy().copy()
 
 
 def make_inputs(K, N, w_bit, group, dt, asym, act_order, seed):

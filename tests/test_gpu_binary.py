@@ -68,8 +68,8 @@ def test_mm_and_layer():
     layer.train()
     xin = torch.randn((16, 256), device="cuda", generator=g, requires_grad=True)
     out = layer(xin)
-    exp = _ref(xin + layer.bias_a, layer.weight.data.float()) * layer.scale_a.double() * layer.scale_w.double()
-    assert torch.allclose(out.double(), exp, rtol=1e-6, atol=1e-6)
+    exp = _ref((xin + layer.bias_a).detach(), layer.weight.data.float()) * layer.scale_a.detach().double() * layer.scale_w.double()
+    assert torch.allclose(out.detach().double(), exp, rtol=1e-6, atol=1e-6)
     out.sum().backward()
     assert xin.grad is not None and layer.scale_a.grad is not None
     layer.eval()
