@@ -58,7 +58,7 @@ def test_mpq_update_matches_reference(case):
         got = nbit.unpack_int(qp.data.cpu().numpy(), w_bit).astype(np.int64)
         exp = nbit.unpack_int(Z[f"{name}_qweight{it}"], w_bit).astype(np.int64)
         diff = np.abs(got - exp)
-        assert diff.max() <= 1 and (diff != 0).mean() <= code_tol, f"step {it}: {(diff != 0).mean():.2e} codes differ"
+        assert diff.max() <= (1 if odt == "f32" else 2) and (diff != 0).mean() <= code_tol, f"step {it}: {(diff != 0).mean():.2e} codes differ"
         zg = nbit.unpack_zeros_asym(qp.zeros.cpu().numpy(), w_bit)
         ze = nbit.unpack_zeros_asym(Z[f"{name}_zeros{it}"], w_bit)
         ztol = 0.0 if it < 5 else (0.1 if w_bit == 8 else (5e-3 if odt == "f32" else 5e-2))
