@@ -41,6 +41,27 @@ def algorithmic_bytes(K, N, M=1, w_bit=W_BIT, group=GROUP):
     return K * N * w_bit // 8 + 2 * (K // group) * N * 2 + 2 * M * K + 2 * M * N
 
 
+def rank_seed(rank):
+    """every rank serves its own request stream: distinct weights / activations per rank (weak scaling, replicas)."""
+    return 1234 + 7919 * rank
+
+
+def whole_job_rate(world, steps, ms):
+    """units (tokens) all ranks processed / the slowest rank's time."""
+    return world * steps / (ms / 1e3)
+
+
+def max_over_ranks(values, world, device):
+    """max over ranks of per-rank device times (no data-path collective anywhere else: the path shards by replica)."""
+    if world == 1:
+        return [float(v) for v in values]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -214,7 +235,7 @@ def main():
         L, wps, sk = (int(v) for v in tune.split(","))
         _cabi.check(_cabi.lib().b200bit_set_gemv_tuning(L, wps, sk))
 
-    layers = build_model(dev, seed=rank)
+    layers = build_model(dev, seed=rank_seed(rank))
     h, inter = LLAMA7B["hidden"], LLAMA7B["inter"]
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     x_h = torch.randn((1, h), device=dev, generator=g).half()
@@ -278,15 +299,12 @@ def main():
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e = max_over_ranks([ms, ms_e2e], world, dev)
 
     if rank == 0:
         ms_step = ms / args.steps
-        tok_s = world * args.steps / (ms / 1e3)
-        e2e_tok_s = world * args.steps / (ms_e2e / 1e3)
+        tok_s = whole_job_rate(world, args.steps, ms)
+        e2e_tok_s = whole_job_rate(world, args.steps, ms_e2e)
         tok_bytes = sum(algorithmic_bytes(K, N) for _, K, N, *_ in layers)
         peak, peak_src = hbm_peak()
         per_launch_us = ms_step * 1e3 / n_launch
