@@ -48,8 +48,8 @@ def test_mpq_update_matches_reference(case):
         torch.cuda.synchronize()
         m_ref, v_ref = _dev(Z[f"{name}_m{it}"]).float().cpu().numpy(), _dev(Z[f"{name}_v{it}"]).float().cpu().numpy()
         rt = 1e-6 if odt == "f32" else 1e-2
-        np.testing.assert_allclose(m.float().cpu().numpy(), m_ref, rtol=rt, atol=1e-12 if odt == "f32" else 1e-6)
-        np.testing.assert_allclose(v.float().cpu().numpy(), v_ref, rtol=rt, atol=1e-12 if odt == "f32" else 1e-6)
+        np.testing.assert_allclose(m.float().cpu().numpy(), m_ref, rtol=rt, atol=1e-12 if odt == "f32" else 5e-6)
+        np.testing.assert_allclose(v.float().cpu().numpy(), v_ref, rtol=rt, atol=1e-12 if odt == "f32" else 5e-6)   # v ~ 1e-7: half subnormals
         if w_bit == 8 and it == 6:
             # 8-bit zero points are ~200: zq + step*ng lies within one fp32 ulp of an integer, so the reference's
             # trunc(mean(...)) at step 5 depends on the summation order (5 % of the zero points flip by one between torch
