@@ -6,6 +6,7 @@
 #include "mpq_gemv.cuh"
 #include "mpq_mma.cuh"
 #include "mpq_stream.cuh"
+#include "mpq_umma.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -398,6 +399,54 @@ static StreamPlan plan_stream(int M, int K, int N, int G, int w_bit, int asym, i
     return pl;
 }
 
+struct UmmaPlan {
+    bool ok;
+    int FJ2, ngr, rpr, rpr_shift, strips, rps, steps, grid, S;
+    size_t smem;
+};
+
+// tcgen05 small-batch kernel (mpq_umma.cuh): f16, 4-bit, contiguous groups of 64 / 128 / multiples of 256, M <= 4 per pass
+static UmmaPlan plan_umma(int M, int K, int N, int G, int w_bit, int asym, int dtype, bool trivial_gidx) {
+    UmmaPlan pl{};
+    pl.ok = false;
+    if (!trivial_gidx || dtype != B200BIT_F16 || w_bit != 4) return pl;
+    const int nb = 8;
+    if (N % 32 != 0 || K % (nb * 32) != 0 || K % G != 0) return pl;
+    if (asym && N % (4 * nb) != 0) return pl;
+    const int gs = K / G;
+    if (gs % nb != 0) return pl;
+    const int rpg = gs / nb;
+    if (rpg == 8 || rpg == 16) {
+        pl.FJ2 = rpg / 8; pl.ngr = 32 / rpg; pl.rpr = 1; pl.rpr_shift = 0;
+    } else if (rpg % 32 == 0) {
+        pl.FJ2 = 4; pl.ngr = 1; pl.rpr = rpg / 32; pl.rpr_shift = -1;
+        for (int sh = 0; sh < 30; ++sh) if ((1 << sh) == pl.rpr) pl.rpr_shift = sh;
+    } else {
+        return pl;
+    }
+    pl.strips = N / 32;
+    pl.rps = (K / nb) / 32;
+    if (pl.rps < 4) return pl;
+    pl.steps = (pl.rps + 3) / 4;
+    int grid = sm_count();
+    if (grid > pl.strips) grid = pl.strips;
+    pl.grid = grid;
+    const int strips_max = (pl.strips + grid - 1) / grid;
+    const int mm = M < UM_MB ? M : UM_MB;
+    const size_t fixed = size_t(pl.steps) * 8192 + ((size_t(mm) * 4 * pl.steps * (4 / pl.FJ2) + 3) & ~size_t(3)) * 4 +
+                         4 * UM_MB * 32 * 4 + 1024;
+    int S = g_tune_warps > 0 ? g_tune_warps : 6;
+    const int total = strips_max * pl.steps;
+    if (S > total) S = total;
+    if (S < 2) S = 2;
+    for (; S >= 2; --S) {
+        pl.S = S;
+        pl.smem = fixed + size_t(S) * 4 * (UM_TILE + UM_SZ) + size_t(8 * S + 16) * 8;
+        if (pl.smem <= 220 * 1024) { pl.ok = true; break; }
+    }
+    return pl;
+}
+
 static int launch_stream(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tz, const StreamParams& p,
                          const StreamLaunch& l, int w_bit) {
     switch (w_bit) {
@@ -438,7 +487,7 @@ int b200bit_set_gemv_tuning(int L, int warps, int splitk) {
 /* path override for benchmarks/tests: 0 auto, 1 CUDA-core GEMV, 2 small-batch mma kernel, 3 general fallback;
  * mma_for_m1: in auto mode route M == 1 to the mma kernel (1) or to the CUDA-core GEMV (0) */
 int b200bit_set_path(int path, int mma_for_m1) {
-    B200_REQUIRE(path >= 0 && path <= 4, B200BIT_ERR_ARG, "path must be in [0,4]");
+    B200_REQUIRE(path >= 0 && path <= 5, B200BIT_ERR_ARG, "path must be in [0,5]");
     g_path = path;
     g_mma_for_m1 = mma_for_m1 ? 1 : 0;
     return B200BIT_OK;
@@ -477,6 +526,36 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
     const bool trivial = (g_idx == nullptr);
     // ---- path selection: TMA-streamed tensor kernel (f16, M <= 32) > mma.sync kernel > CUDA-core GEMV > general ----
     // auto: M == 1 -> CUDA-core FHFMA GEMV (fastest measured at batch 1, profiles/r1_*); 2 <= M: TMA-streamed tensor kernel
+    const UmmaPlan up = (g_path == 5) ? plan_umma(M, K, N, G, w_bit, asym, dtype, trivial) : UmmaPlan{};
+    if (up.ok) {
+        CUtensorMap tw, ts, tz;
+        int rc = make_map_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_UINT32, qweight, uint64_t(N), uint64_t(K / nb), uint64_t(N) * 4,
+                             32, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        rc = make_map_2d(&ts, CU_TENSOR_MAP_DATA_TYPE_UINT16, scales, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
+                         uint32_t(up.ngr), CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        if (asym)
+            rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT32, zeros, uint64_t(N / nb), uint64_t(G),
+                             uint64_t(N / nb) * 4, uint32_t(32 / nb), uint32_t(up.ngr), CU_TENSOR_MAP_SWIZZLE_NONE);
+        else
+            rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT16, zeros, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
+                             uint32_t(up.ngr), CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        for (int m0 = 0; m0 < M; m0 += UM_MB) {
+            const int mc = (M - m0) < UM_MB ? (M - m0) : UM_MB;
+            UmmaParams p{};
+            p.x = reinterpret_cast<const uint16_t*>(x) + size_t(m0) * K;
+            p.y = reinterpret_cast<uint16_t*>(y) + size_t(m0) * N;
+            p.M = mc; p.K = K; p.N = N; p.strips = up.strips; p.rps = up.rps; p.steps = up.steps; p.ngr = up.ngr;
+            p.rpr = up.rpr; p.rpr_shift = up.rpr_shift; p.asym = asym; p.S = up.S; p.trace = g_trace;
+            UmmaLaunch l{};
+            l.FJ2 = up.FJ2; l.grid = up.grid; l.smem = up.smem; l.flags = flags; l.stream = stream;
+            rc = launch_umma(tw, ts, tz, p, l);
+            if (rc != B200BIT_OK) return rc;
+        }
+        return B200BIT_OK;
+    }
     const StreamPlan sp = (g_path == 4 || (g_path == 0 && M >= 2)) ? plan_stream(M, K, N, G, w_bit, asym, dtype, trivial)
                                                                  : StreamPlan{};
     if (sp.ok) {
