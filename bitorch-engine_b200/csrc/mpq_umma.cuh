@@ -48,13 +48,31 @@ struct UmmaParams {
 
 __device__ __forceinline__ void um_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void um_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void um_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// The MMA warp runs its loop CONVERGED (all 32 lanes wait on the barriers) and only the tcgen05 instruction itself is
+// predicated on the elected lane: issued from a divergent `if (lane == 0)` region the compiler wraps every UTCHMMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop that costs ~110 cycles per instruction (tools/umma_rate.cu).
+__device__ __forceinline__ uint32_t um_elect() {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+    return leader;
 }
-__device__ __forceinline__ void um_mma(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc),
-                 "r"(accumulate) : "memory");
+__device__ __forceinline__ void um_expect_tx(uint64_t* bar, unsigned bytes, uint32_t leader) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void um_tma_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint32_t leader) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void um_commit(uint64_t* bar, uint32_t leader) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void um_mma(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc),
+                 "r"(accumulate), "r"(leader) : "memory");
 }
 __device__ __forceinline__ void um_st16(uint32_t addr, const uint32_t (&r)[16]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -86,6 +104,7 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
     unsigned char* smem_raw = um_smem_raw + ((128u - (smem_u32(um_smem_raw) & 127u)) & 127u);   // TMA destinations: 128 B
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, G = gridDim.x, S = p.S;
+    ST_TRACE(0);
 
     // ---- shared memory ----
     unsigned char* wst = smem_raw;                                        // [S][4 slices][4096]
@@ -122,6 +141,7 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
     um_fence_before();
     __syncthreads();
     um_fence_after();
+    ST_TRACE(1);
     const uint32_t tmem = *tmem_slot;
     const uint32_t tm_d = tmem;                  // + dbuf*32 + class*16
     const uint32_t tm_a = tmem + 64;             // + abuf*32 + class*16
@@ -129,14 +149,16 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
     const unsigned tile_bytes = UM_TILE + unsigned(p.ngr) * 64u + (p.asym ? unsigned(p.ngr) * 16u : unsigned(p.ngr) * 64u);
 
     if (warp == 4) {
-        // =========================== producer: lane s streams K-quarter s ===========================
-        if (lane < 4) {
-            const int s = lane;
-            const int r0 = um_slice_r0(s, p.rps), nr = um_slice_runs(s, p.rps);
-            int ts = 0;                                             // real (non-padded) steps of this K-quarter so far
-            for (int st = 0; st < nstrips; ++st) {
-                const int strip = s_lo + st;
-                for (int pstep = 0; pstep < nr; ++pstep, ++ts) {     // padded steps carry no tile (the consumer writes zeros)
+        // =========================== producer (converged warp, elected lane issues the TMA) ===========================
+        const uint32_t leader = um_elect();
+        for (int st = 0; st < nstrips; ++st) {
+            const int strip = s_lo + st;
+            for (int pstep = 0; pstep < p.steps; ++pstep) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int r0 = um_slice_r0(s, p.rps), nr = um_slice_runs(s, p.rps);
+                    if (pstep >= nr) continue;                     // padded step: no tile (the consumer writes zeros)
+                    const int ts = st * nr + pstep;                // real steps of this K-quarter so far
                     const int slot = ts % S;
                     if (ts >= S) mbar_wait(&wempty[slot * 4 + s], ((ts / S) - 1) & 1);
                     const int kr = r0 + pstep;
@@ -144,19 +166,21 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
                     if (p.ngr > 1 || p.rpr == 1) g0 = kr * p.ngr;
                     else g0 = (p.rpr_shift >= 0) ? (kr >> p.rpr_shift) : (kr / p.rpr);
                     uint64_t* bar = &wfull[slot * 4 + s];
-                    mbar_expect_tx(bar, tile_bytes);
-                    tma_load_2d(wst + (size_t(slot) * 4 + s) * UM_TILE, &tm_w, strip * 32, kr * 32, bar);
+                    um_expect_tx(bar, tile_bytes, leader);
+                    um_tma_2d(wst + (size_t(slot) * 4 + s) * UM_TILE, &tm_w, strip * 32, kr * 32, bar, leader);
                     unsigned char* sz = szst + (size_t(slot) * 4 + s) * UM_SZ;
-                    tma_load_2d(sz, &tm_s, strip * 32, g0, bar);
-                    tma_load_2d(sz + 256, &tm_z, p.asym ? strip * (32 / NB) : strip * 32, g0, bar);
+                    um_tma_2d(sz, &tm_s, strip * 32, g0, bar, leader);
+                    um_tma_2d(sz + 256, &tm_z, p.asym ? strip * (32 / NB) : strip * 32, g0, bar, leader);
                 }
             }
         }
     } else if (warp == 5) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        {
+            const uint32_t leader = um_elect();
             mbar_wait(bready, 0);
             um_fence_after();
+            ST_TRACE(2);
             const uint32_t idesc = (1u << 4) | ((uint32_t(UM_NMMA) >> 3) << 17) | ((128u >> 4) << 24);
             const uint64_t desc_hi = (uint64_t(128 >> 4) << 16) | (uint64_t(256 >> 4) << 32) | (uint64_t(1) << 46);
             const uint32_t bt_addr = smem_u32(bt);
@@ -178,12 +202,14 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
                             const uint32_t boff = uint32_t((((pstep * 4 + q) * 2 + c) * 2 + u) * 512);
                             const uint64_t bdesc = desc_hi | uint64_t(((bt_addr + boff) & 0x3FFFF) >> 4);
                             um_mma(tm_d + dbuf * 32 + c * 16, tm_a + abuf * 32 + c * 16 + u * 8, bdesc, idesc,
-                                   (first && u == 0) ? 0u : 1u);
+                                   (first && u == 0) ? 0u : 1u, leader);
                         }
-                    um_commit(&aempty[abuf]);
-                    if (last) { um_commit(&dfull[dbuf]); ++cg; }
+                    um_commit(&aempty[abuf], leader);
+                    if (last) { um_commit(&dfull[dbuf], leader); ++cg; }
                 }
+                if (t == 0) ST_TRACE(4);
             }
+            ST_TRACE(5);
         }
     } else {
         // =========================== dequant + epilogue warps: thread <-> TMEM lane (K-quarter s = warp, column n = lane) =====
@@ -191,6 +217,7 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
         const int r0 = um_slice_r0(s, p.rps), nr = um_slice_runs(s, p.rps);
 
         pdl_wait_primary();   // x is produced by the previous kernel
+        ST_TRACE(2);
 
         // ---- stage B (x in UMMA core-matrix order, class split, K permuted) and the per-group sums of x ----
         {
@@ -200,13 +227,10 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
             const int krows = p.K / NB;                         // packed rows over K
             const int total = p.M * krows;                      // multiple of 32
             constexpr int SEG_ROWS = 8 * FJ2;
-            for (int i0 = warp * 32; i0 < total; i0 += 128) {
-                const int i = i0 + lane;
+            auto stage_one = [&](int i, const uint4 v) {
                 const int m = i / krows, row = i - m * krows;
-                const uint4 v = *reinterpret_cast<const uint4*>(p.x + size_t(m) * p.K + size_t(row) * NB);
                 const int run = row >> 5, rl = row & 31;
-                // K-quarter of this run
-                int sl = 0;
+                int sl = 0;                                      // K-quarter of this run
 #pragma unroll
                 for (int q = 1; q < 4; ++q) sl += (run >= um_slice_r0(q, p.rps)) ? 1 : 0;
                 const int pstep = run - um_slice_r0(sl, p.rps);
@@ -226,9 +250,17 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
 #pragma unroll
                 for (int off = 1; off < SEG_ROWS; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
                 if ((rl % SEG_ROWS) == 0) xseg[(m * 4 + sl) * nseg_slice + pstep * GPS + rl / SEG_ROWS] = sum;
+            };
+            const uint4* xv = reinterpret_cast<const uint4*>(p.x);       // chunk i = 8 halves; [M, K] is contiguous
+            int i0 = warp * 32 + lane;
+            for (; i0 + 3 * 128 < total; i0 += 4 * 128) {               // 4 loads in flight per thread
+                const uint4 v0 = xv[i0], v1 = xv[i0 + 128], v2 = xv[i0 + 256], v3 = xv[i0 + 384];
+                stage_one(i0, v0); stage_one(i0 + 128, v1); stage_one(i0 + 256, v2); stage_one(i0 + 384, v3);
             }
+            for (; i0 < total; i0 += 128) stage_one(i0, xv[i0]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // B is read by the tensor core (async proxy)
             mbar_arrive(bready);
+            ST_TRACE(3);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");   // xseg visible to all dequant warps
 
@@ -279,6 +311,7 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
                 const bool real = pstep < nr;
                 const unsigned char* wt = wst + (size_t(slot) * 4 + s) * UM_TILE;
                 if (real) mbar_wait(&wfull[slot * 4 + s], (ts / S) & 1);
+                if (st == 0 && pstep == 0) ST_TRACE(4);
 #pragma unroll 1
                 for (int q = 0; q < 4; ++q, ++css) {
                     const int abuf = css % UM_NBUF;
@@ -313,9 +346,11 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
                 if (rel_slot >= 0 && lane == 0) mbar_arrive(&wempty[rel_slot * 4 + s]);
                 rel_slot = -1;
                 if (real) { rel_slot = slot; ++ts; }
+                if (st == 0 && pstep == 0) ST_TRACE(5);
             }
             // strip done: flush the last pending group before the epilogue of this strip
             if (pend_valid) { flush(pend_slot, pend_gi, pend_pstep, pend_real); pend_valid = false; }
+            ST_TRACE(6);
             // ---- combine the 4 K-quarters (fixed order) and write y ----
 #pragma unroll
             for (int m = 0; m < UM_MB; ++m)
@@ -333,6 +368,7 @@ __global__ void __launch_bounds__(192, 1) mpq_umma_kernel(const __grid_constant_
     }
     um_fence_before();
     __syncthreads();
+    ST_TRACE(7);
     if (warp == 5) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(UM_TMEM_COLS) : "memory");
     }

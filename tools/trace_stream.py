@@ -12,11 +12,13 @@ ap.add_argument("--shape", default="4096x4096")
 ap.add_argument("--pdl", type=int, default=1)
 ap.add_argument("--tune", default="0:0:0")
 ap.add_argument("--chain", type=int, default=6)
+ap.add_argument("--path", type=int, default=4)
+ap.add_argument("--M", type=int, default=1)
 args = ap.parse_args()
 K, N = (int(v) for v in args.shape.split("x"))
 dev = torch.device("cuda:0")
 lib = _cabi.lib()
-lib.b200bit_set_path(4, 1)
+lib.b200bit_set_path(args.path, 1)
 L, wp, sk = (int(v) for v in args.tune.split(":"))
 lib.b200bit_set_gemv_tuning(L, wp, sk)
 g = torch.Generator(device=dev).manual_seed(0)
@@ -26,7 +28,7 @@ for i in range(args.chain):
     sc = (torch.rand((K // 128, N), device=dev, generator=g) * 0.01 + 0.005).half()
     ws.append((qw, sc, (sc.float() * 8).half()))
 gi = torch.arange(K, dtype=torch.int32, device=dev) // 128
-x = torch.randn((1, K), device=dev, generator=g).half()
+x = torch.randn((args.M, K), device=dev, generator=g).half()
 trace = torch.zeros((args.chain, 148 * 16 * 8), dtype=torch.int64, device=dev)
 stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
@@ -51,6 +53,7 @@ for node in range(2, args.chain):
     tn = t[node]
     print(f"node {node}: (ns relative to node 2 first stamp; min / median / max over CTAs x warps that wrote the stamp)")
     for si, nm in enumerate(names):
-        v = tn[:, :, si]; v = v[v > 0] - base
-        if v.numel():
-            print(f"   {nm:8s} min {int(v.min()):7d}  med {int(v.median()):7d}  max {int(v.max()):7d}   n={v.numel()}")
+        for wsel, wname in ((slice(0, 4), "w0-3"), (slice(4, 5), "w4"), (slice(5, 6), "w5"), (slice(6, 16), "w6+")):
+            v = tn[:, wsel, si]; v = v[v > 0] - base
+            if v.numel():
+                print(f"   {nm:8s} {wname:5s} min {int(v.min()):7d}  med {int(v.median()):7d}  max {int(v.max()):7d}   n={v.numel()}")
