@@ -19,7 +19,7 @@ LIB = os.path.join(LIBDIR, "libb200bit.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false",
-          "-Xcompiler", "-fvisibility=hidden", "-DB200BIT_BUILD"]
+          "-Xcompiler", "-fvisibility=hidden", "-DB200BIT_BUILD"] + os.environ.get("B200BIT_EXTRA_CFLAGS", "").split()
 
 
 def _sources():

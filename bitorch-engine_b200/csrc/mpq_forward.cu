@@ -401,11 +401,11 @@ static StreamPlan plan_stream(int M, int K, int N, int G, int w_bit, int asym, i
 
 struct UmmaPlan {
     bool ok;
-    int FJ2, ngr, rpr, rpr_shift, strips, rps, steps, grid, S;
-    size_t smem;
+    int FJ2, MB, ngr, rpr, rpr_shift, strips, rps, steps, grid, S;
+    size_t smem, img_bytes, xsum_bytes;
 };
 
-// tcgen05 small-batch kernel (mpq_umma.cuh): f16, 4-bit, contiguous groups of 64 / 128 / multiples of 256, M <= 4 per pass
+// tcgen05 batched kernel (mpq_umma.cuh): f16, 4-bit, contiguous groups of 64 / 128 / multiples of 256, <= 32 rows per pass
 static UmmaPlan plan_umma(int M, int K, int N, int G, int w_bit, int asym, int dtype, bool trivial_gidx) {
     UmmaPlan pl{};
     pl.ok = false;
@@ -432,17 +432,23 @@ static UmmaPlan plan_umma(int M, int K, int N, int G, int w_bit, int asym, int d
     if (grid > pl.strips) grid = pl.strips;
     pl.grid = grid;
     const int strips_max = (pl.strips + grid - 1) / grid;
-    const int mm = M < UM_MB ? M : UM_MB;
-    const size_t fixed = size_t(pl.steps) * 8192 + ((size_t(mm) * 4 * pl.steps * (4 / pl.FJ2) + 3) & ~size_t(3)) * 4 +
-                         4 * UM_MB * 32 * 4 + 1024;
-    int S = g_tune_warps > 0 ? g_tune_warps : 6;
+    const int mm = M < 32 ? M : 32;
+    pl.MB = mm <= 4 ? 4 : mm <= 8 ? 8 : mm <= 16 ? 16 : 32;
+    if (g_tune_splitk == 4 || g_tune_splitk == 8 || g_tune_splitk == 16 || g_tune_splitk == 32)       // sweep hook
+        if (g_tune_splitk >= mm) pl.MB = g_tune_splitk;
+    const int nmma = 4 * pl.MB, gps = 4 / pl.FJ2;
+    pl.img_bytes = size_t(pl.steps) * nmma * 512;
+    pl.xsum_bytes = (size_t(pl.MB) * 4 * pl.steps * gps * 4 + 127) & ~size_t(127);
+    const size_t fixed = size_t(UM_BSTAGES) * nmma * 512 + ((size_t(pl.MB) * 4 * pl.steps * gps + 3) & ~size_t(3)) * 4 +
+                         size_t(4) * pl.MB * 32 * 4 + 1024;
+    int S = g_tune_warps > 0 ? g_tune_warps : 5;
     const int total = strips_max * pl.steps;
-    if (S > total) S = total;
+    if (S > total + 1) S = total + 1;
     if (S < 2) S = 2;
     for (; S >= 2; --S) {
         pl.S = S;
-        pl.smem = fixed + size_t(S) * 4 * (UM_TILE + UM_SZ) + size_t(8 * S + 16) * 8;
-        if (pl.smem <= 220 * 1024) { pl.ok = true; break; }
+        pl.smem = fixed + size_t(S) * 4 * (UM_TILE + UM_SZ) + size_t(8 * S + 40) * 8;
+        if (pl.smem <= 225 * 1024) { pl.ok = true; break; }
     }
     return pl;
 }
@@ -500,10 +506,13 @@ int b200bit_set_trace_buffer(void* buf) {
 }
 
 size_t b200bit_mpq_forward_workspace_bytes(int M, int K, int N, int w_bit) {
-    (void)K; (void)w_bit;
+    (void)w_bit;
     const int mm = M < 32 ? M : 32;
-    // tickets | split-K / shared-strip partials (<= 64 contributions of [mm, N] f32)
-    return size_t(B200BIT_WS_TICKET_BYTES) + size_t(64) * mm * N * sizeof(float);
+    // tickets | the larger of: split-K / shared-strip partials (<= 64 contributions of [mm, N] f32),
+    //                          tcgen05 path: B image (<= 64 KB per 1024 K elements at 32 batch slots) + per-group sums of x
+    const size_t partials = size_t(64) * mm * N * sizeof(float);
+    const size_t image = (size_t(K) / 1024 + 1) * 65536 + (size_t(K) / 64 + 1) * 32 * 4 * sizeof(float) + 4096;
+    return size_t(B200BIT_WS_TICKET_BYTES) + (partials > image ? partials : image);
 }
 
 int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scales, const void* zeros,
@@ -527,7 +536,7 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
     // ---- path selection: TMA-streamed tensor kernel (f16, M <= 32) > mma.sync kernel > CUDA-core GEMV > general ----
     // auto: M == 1 -> CUDA-core FHFMA GEMV (fastest measured at batch 1, profiles/r1_*); 2 <= M: TMA-streamed tensor kernel
     const UmmaPlan up = (g_path == 5) ? plan_umma(M, K, N, G, w_bit, asym, dtype, trivial) : UmmaPlan{};
-    if (up.ok) {
+    if (up.ok && workspace && workspace_bytes >= size_t(B200BIT_WS_TICKET_BYTES) + up.img_bytes + up.xsum_bytes) {
         CUtensorMap tw, ts, tz;
         int rc = make_map_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_UINT32, qweight, uint64_t(N), uint64_t(K / nb), uint64_t(N) * 4,
                              32, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -542,15 +551,23 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
             rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT16, zeros, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
                              uint32_t(up.ngr), CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc != B200BIT_OK) return rc;
-        for (int m0 = 0; m0 < M; m0 += UM_MB) {
-            const int mc = (M - m0) < UM_MB ? (M - m0) : UM_MB;
+        unsigned char* img = reinterpret_cast<unsigned char*>(workspace) + B200BIT_WS_TICKET_BYTES;
+        float* xsum = reinterpret_cast<float*>(img + up.img_bytes);
+        for (int m0 = 0; m0 < M; m0 += up.MB) {
+            const int mc = (M - m0) < up.MB ? (M - m0) : up.MB;
+            UmmaPrepParams pp{};
+            pp.x = reinterpret_cast<const uint16_t*>(x) + size_t(m0) * K;
+            pp.bimg = img; pp.xsum = xsum; pp.M = mc; pp.K = K; pp.MB = up.MB; pp.rps = up.rps; pp.steps = up.steps;
+            pp.fj2 = up.FJ2;
+            rc = launch_umma_prepare(pp, flags, stream);
+            if (rc != B200BIT_OK) return rc;
             UmmaParams p{};
-            p.x = reinterpret_cast<const uint16_t*>(x) + size_t(m0) * K;
+            p.bimg = img; p.xsum = xsum;
             p.y = reinterpret_cast<uint16_t*>(y) + size_t(m0) * N;
             p.M = mc; p.K = K; p.N = N; p.strips = up.strips; p.rps = up.rps; p.steps = up.steps; p.ngr = up.ngr;
             p.rpr = up.rpr; p.rpr_shift = up.rpr_shift; p.asym = asym; p.S = up.S; p.trace = g_trace;
             UmmaLaunch l{};
-            l.FJ2 = up.FJ2; l.grid = up.grid; l.smem = up.smem; l.flags = flags; l.stream = stream;
+            l.FJ2 = up.FJ2; l.MB = up.MB; l.grid = up.grid; l.smem = up.smem; l.flags = flags; l.stream = stream;
             rc = launch_umma(tw, ts, tz, p, l);
             if (rc != B200BIT_OK) return rc;
         }
@@ -583,6 +600,7 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
             p.zero_page = reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(workspace) + B200BIT_WS_ZERO_OFFSET);
             p.M = mc; p.K = K; p.N = N; p.strips = sp.strips; p.rps = sp.rps; p.ngr = sp.ngr; p.rpr = sp.rpr;
             p.rpr_shift = sp.rpr_shift; p.asym = asym; p.S = sp.S; p.maxseg = sp.maxseg; p.trace = g_trace; p.debug_no_x = (g_tune_L == 16);
+            { static const int pm = getenv("B200BIT_STREAM_PRODUCER") ? atoi(getenv("B200BIT_STREAM_PRODUCER")) : 0; p.producer_mode = pm; }
             StreamLaunch l{};
             l.MT = (mc + 7) / 8; l.FJ = sp.FJ; l.warps = sp.warps; l.grid = sp.grid; l.xs = sp.xs;
             l.smem = sp.smem; l.flags = flags; l.stream = stream;

@@ -42,6 +42,7 @@ struct StreamParams {
     int S;               // ring stages
     int maxseg;          // partial-sum slots per consumer warp (<= ST_MAXSEG)
     int debug_no_x;      // diagnostics: read x fragments from the zero page (timing experiments only)
+    int producer_mode;           // 0: lane w feeds warp w (independent waits); 1: converged warp, elected-lane issue
     unsigned long long* trace;   // optional [grid][16 warps][8] globaltimer stamps (diagnostics; nullptr = off)
 };
 
@@ -68,6 +69,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+// Uniform-datapath instructions (UTMALDG, UTCHMMA, UTCBAR) must be issued from CONVERGED code with only the instruction
+// itself predicated on an elected lane: inside a divergent region (`if (lane == 0)`, per-lane loops) the compiler wraps
+// every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop that costs ~100 cycles per instruction and serialises
+// the active lanes (measured: tools/umma_rate.cu, 114 -> 13 cycles per tcgen05.mma).
+__device__ __forceinline__ uint32_t um_elect() {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+    return leader;
+}
+__device__ __forceinline__ void um_expect_tx(uint64_t* bar, unsigned bytes, uint32_t leader) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void um_tma_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint32_t leader) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "r"(leader) : "memory");
 }
 
 __device__ __forceinline__ unsigned long long st_gtime() {
@@ -144,28 +164,60 @@ __global__ void __launch_bounds__(XS ? 544 : 288, 1) mpq_stream_kernel(const __g
     const unsigned stage_bytes = ST_TILE_BYTES + unsigned(p.ngr) * 64u + (p.asym ? unsigned(p.ngr) * (128u / NB) : unsigned(p.ngr) * 64u);
 
     if (warp == NW) {
-        // =========================== producer: lane w feeds consumer warp w ===========================
-        // warp w's k-th run lives in ring slot (k % depth) * NW + w, depth = S / NW: every slot has exactly one producer
-        // lane and one consumer warp, so the empty/full phases of a slot are always used in order.
-        if (lane < NW) {
-            const int w = lane;
-            const int cnt_w = q0 + (w < rem ? 1 : 0);
-            const int wlo = lo + w * q0 + min(w, rem);
-            int strip = (cnt_w > 0) ? wlo / p.rps : 0;
-            int kr = wlo - strip * p.rps;
-            const int depth = S / NW;                 // ring slots owned by this lane: (k % depth) * NW + w
-            for (int k = 0; k < cnt_w; ++k) {
-                const int slot = (k % depth) * NW + w;
-                if (k >= depth) mbar_wait(&empty[slot], ((k / depth) - 1) & 1);
-                int g0;
-                if (p.ngr > 1 || p.rpr == 1) g0 = kr * p.ngr;
-                else g0 = (p.rpr_shift >= 0) ? (kr >> p.rpr_shift) : (kr / p.rpr);
-                mbar_expect_tx(&full[slot], stage_bytes);
-                tma_load_2d(wst + size_t(slot) * ST_TILE_BYTES, &tm_w, strip * 32, kr * ST_RUN_ROWS, &full[slot]);
-                unsigned char* sz = szst + size_t(slot) * ST_SZ_BYTES;
-                tma_load_2d(sz, &tm_s, strip * 32, g0, &full[slot]);
-                tma_load_2d(sz + 256, &tm_z, p.asym ? strip * (32 / NB) : strip * 32, g0, &full[slot]);
-                if (++kr == p.rps) { kr = 0; ++strip; }
+        if (p.producer_mode == 0 || p.producer_mode == 2) {
+            // =========================== producer: lane w feeds consumer warp w ===========================
+            // warp w's k-th run lives in ring slot (k % depth) * NW + w, depth = S / NW: every slot has exactly one producer
+            // lane and one consumer warp, so the empty/full phases of a slot are always used in order.
+            if (lane < NW) {
+                const int w = lane;
+                const int cnt_w = q0 + (w < rem ? 1 : 0);
+                const int wlo = lo + w * q0 + min(w, rem);
+                int strip = (cnt_w > 0) ? wlo / p.rps : 0;
+                int kr = wlo - strip * p.rps;
+                const int depth = S / NW;                 // ring slots owned by this lane: (k % depth) * NW + w
+                for (int k = 0; k < cnt_w; ++k) {
+                    const int slot = (k % depth) * NW + w;
+                    if (k >= depth) mbar_wait(&empty[slot], ((k / depth) - 1) & 1);
+                    int g0;
+                    if (p.ngr > 1 || p.rpr == 1) g0 = kr * p.ngr;
+                    else g0 = (p.rpr_shift >= 0) ? (kr >> p.rpr_shift) : (kr / p.rpr);
+                    if (p.producer_mode == 2) {      // timing experiment: weight tile only (results are wrong)
+                        mbar_expect_tx(&full[slot], ST_TILE_BYTES);
+                        tma_load_2d(wst + size_t(slot) * ST_TILE_BYTES, &tm_w, strip * 32, kr * ST_RUN_ROWS, &full[slot]);
+                    } else {
+                    mbar_expect_tx(&full[slot], stage_bytes);
+                    tma_load_2d(wst + size_t(slot) * ST_TILE_BYTES, &tm_w, strip * 32, kr * ST_RUN_ROWS, &full[slot]);
+                    unsigned char* sz = szst + size_t(slot) * ST_SZ_BYTES;
+                    tma_load_2d(sz, &tm_s, strip * 32, g0, &full[slot]);
+                    tma_load_2d(sz + 256, &tm_z, p.asym ? strip * (32 / NB) : strip * 32, g0, &full[slot]);
+                    }
+                    if (++kr == p.rps) { kr = 0; ++strip; }
+                }
+            }
+        } else {
+            // =========================== alternative producer (converged warp; the elected lane issues every TMA) ===========================
+            // warp w's k-th run lives in ring slot (k % depth) * NW + w, depth = S / NW: every slot has exactly one consumer
+            // warp, so the empty/full phases of a slot are always used in order.  Issue order is k-major (the order of use).
+            const uint32_t leader = um_elect();
+            const int depth = S / NW;
+            const int kmax = q0 + (rem > 0 ? 1 : 0);
+            for (int k = 0; k < kmax; ++k) {
+                for (int w = 0; w < NW; ++w) {
+                    if (k >= q0 + (w < rem ? 1 : 0)) continue;
+                    const int run = lo + w * q0 + min(w, rem) + k;
+                    const int strip = run / p.rps;
+                    const int kr = run - strip * p.rps;
+                    const int slot = (k % depth) * NW + w;
+                    if (k >= depth) mbar_wait(&empty[slot], ((k / depth) - 1) & 1);
+                    int g0;
+                    if (p.ngr > 1 || p.rpr == 1) g0 = kr * p.ngr;
+                    else g0 = (p.rpr_shift >= 0) ? (kr >> p.rpr_shift) : (kr / p.rpr);
+                    um_expect_tx(&full[slot], stage_bytes, leader);
+                    um_tma_2d(wst + size_t(slot) * ST_TILE_BYTES, &tm_w, strip * 32, kr * ST_RUN_ROWS, &full[slot], leader);
+                    unsigned char* sz = szst + size_t(slot) * ST_SZ_BYTES;
+                    um_tma_2d(sz, &tm_s, strip * 32, g0, &full[slot], leader);
+                    um_tma_2d(sz + 256, &tm_z, p.asym ? strip * (32 / NB) : strip * 32, g0, &full[slot], leader);
+                }
             }
         }
     } else {

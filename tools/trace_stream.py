@@ -53,7 +53,7 @@ for node in range(2, args.chain):
     tn = t[node]
     print(f"node {node}: (ns relative to node 2 first stamp; min / median / max over CTAs x warps that wrote the stamp)")
     for si, nm in enumerate(names):
-        for wsel, wname in ((slice(0, 4), "w0-3"), (slice(4, 5), "w4"), (slice(5, 6), "w5"), (slice(6, 16), "w6+")):
+        for wsel, wname in ((slice(0, 4), "w0-3"), (slice(4, 8), "w4-7"), (slice(8, 12), "w8-11"), (slice(12, 14), "w12-13"), (slice(14, 15), "w14/prod"), (slice(15, 16), "w15/mma")):
             v = tn[:, wsel, si]; v = v[v > 0] - base
             if v.numel():
                 print(f"   {nm:8s} {wname:5s} min {int(v.min()):7d}  med {int(v.median()):7d}  max {int(v.max()):7d}   n={v.numel()}")
