@@ -328,7 +328,7 @@ def main():
                         "d2h_bytes_per_step": y_host.numel() * 2},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "mpq_gemv_kernel<4,f16,M=1>", "avg_launch_us": per_launch_us,
+                             "kernel": "mpq_pipe_kernel<4,f16,FS=4>", "avg_launch_us": per_launch_us,
                              "algorithmic_bytes_per_launch": tok_bytes / n_launch},
                 "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:

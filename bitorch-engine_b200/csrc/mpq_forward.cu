@@ -7,6 +7,8 @@
 #include "mpq_mma.cuh"
 #include "mpq_stream.cuh"
 #include "mpq_umma.cuh"
+#include "mpq_pipe.cuh"
+#include "mpq_pipe_mma.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -42,7 +44,7 @@ int sm_count() {
 // process-wide tuning override for sweeps (0 = heuristic); set through b200bit_set_gemv_tuning()
 static int g_tune_L = 0, g_tune_warps = 0, g_tune_splitk = 0;
 // 0 = auto, 1 = CUDA-core FHFMA GEMV, 2 = mma.sync small-batch kernel, 3 = general fallback,
-// 4 = TMA-streamed small-batch kernel
+// 4 = TMA-streamed small-batch kernel, 5 = tcgen05 batched kernel, 6 = cross-kernel pipelined decode GEMV (mpq_pipe.cuh)
 static int g_path = 0;
 // in auto mode, does M == 1 go to the tensor kernel (1) or stay on the CUDA-core GEMV (0)?
 static int g_mma_for_m1 = 0;
@@ -453,6 +455,74 @@ static UmmaPlan plan_umma(int M, int K, int N, int G, int w_bit, int asym, int d
     return pl;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// cross-kernel pipelined decode GEMV (mpq_pipe.cuh): M == 1, f16 / bf16, contiguous groups
+// ---------------------------------------------------------------------------------------------------------------
+struct PipePlan {
+    bool ok;
+    int FS, rpg, rpg_shift, gps, stages_total, stages_per_split, splitk, S, sz_bytes, s_tile_bytes, z_tile_bytes, strips;
+    size_t smem;
+};
+
+static PipePlan plan_pipe(int M, int K, int N, int G, int w_bit, int asym, int dtype, bool trivial_gidx) {
+    PipePlan pl{};
+    pl.ok = false;
+    if (M != 1 || !trivial_gidx || dtype == B200BIT_F32) return pl;
+    if (w_bit != 2 && w_bit != 4 && w_bit != 8) return pl;
+    if (dtype == B200BIT_BF16 && w_bit > 4) return pl;
+    const int nb = 32 / w_bit;
+    if (N % 32 != 0 || K % (nb * PG_UNIT_ROWS) != 0 || K % G != 0) return pl;
+    if (asym && (w_bit == 2 || N % (4 * nb) != 0)) return pl;       // packed zero rows: TMA box >= 16 B, stride % 16 == 0
+    const int gs = K / G;
+    if (gs % nb != 0) return pl;
+    const int rpg = gs / nb;
+    if (rpg % 4 != 0) return pl;
+    if (rpg >= PG_UNIT_ROWS ? (rpg % PG_UNIT_ROWS != 0) : (PG_UNIT_ROWS % rpg != 0)) return pl;
+    pl.rpg = rpg;
+    pl.rpg_shift = -1;
+    if (rpg <= PG_STAGE_ROWS) {
+        if (PG_STAGE_ROWS % rpg != 0) return pl;
+        for (int sh = 0; sh < 8; ++sh) if ((1 << sh) == rpg) pl.rpg_shift = sh;
+        if (pl.rpg_shift < 0) return pl;
+        pl.gps = PG_STAGE_ROWS / rpg;
+    } else {
+        if (rpg % PG_STAGE_ROWS != 0) return pl;
+        pl.gps = 1;
+    }
+    pl.FS = (rpg < PG_UNIT_ROWS ? rpg : PG_UNIT_ROWS) / 4;
+    pl.s_tile_bytes = pl.gps * 64;
+    pl.z_tile_bytes = asym ? pl.gps * (128 / nb) : pl.gps * 64;
+    pl.sz_bytes = (pl.s_tile_bytes + 127) & ~127;
+    const int R = K / nb;
+    pl.stages_total = (R + PG_STAGE_ROWS - 1) / PG_STAGE_ROWS;
+    pl.strips = N / 32;
+    // split K so that a CTA's packed weights fit its ring whole (everything is requested before griddepcontrol.wait);
+    // sweep hook: g_tune_splitk forces the split, g_tune_warps the ring depth
+    int S = g_tune_warps > 0 ? g_tune_warps : PG_MAX_STAGES;
+    if (S > PG_MAX_STAGES) S = PG_MAX_STAGES;
+    int splitk = g_tune_splitk > 0 ? g_tune_splitk : (pl.stages_total + S - 1) / S;
+    if (splitk > pl.stages_total) splitk = pl.stages_total;
+    if (splitk > 64) splitk = 64;
+    pl.stages_per_split = (pl.stages_total + splitk - 1) / splitk;
+    pl.splitk = (pl.stages_total + pl.stages_per_split - 1) / pl.stages_per_split;
+    if (S > pl.stages_per_split) S = pl.stages_per_split;
+    pl.S = S;
+    const size_t xseg = size_t(pl.stages_per_split) * PG_STAGE_ROWS * nb / 16 * 4;
+    pl.smem = size_t(S) * (PG_TILE_BYTES + 2 * pl.sz_bytes) + 2 * PG_MAX_STAGES * 8 + PG_WARPS * 32 * 4 + xseg + 16;
+    pl.ok = pl.smem <= 76800 && size_t(pl.strips) * sizeof(unsigned) <= B200BIT_WS_ZERO_OFFSET;
+    return pl;
+}
+
+static int launch_pipe(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tz, const PipeParams& p,
+                       const PipeLaunch& l, int w_bit, bool bf16) {
+    switch (w_bit) {
+        case 2: return bf16 ? launch_pipe_family<2, true>(tw, ts, tz, p, l) : launch_pipe_family<2, false>(tw, ts, tz, p, l);
+        case 4: return bf16 ? launch_pipe_family<4, true>(tw, ts, tz, p, l) : launch_pipe_family<4, false>(tw, ts, tz, p, l);
+        case 8: if (!bf16) return launch_pipe_family<8, false>(tw, ts, tz, p, l);
+    }
+    return set_error(B200BIT_ERR_UNSUPPORTED, "pipe gemv: w_bit=%d bf16=%d", w_bit, int(bf16));
+}
+
 static int launch_stream(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tz, const StreamParams& p,
                          const StreamLaunch& l, int w_bit) {
     switch (w_bit) {
@@ -490,10 +560,11 @@ int b200bit_set_gemv_tuning(int L, int warps, int splitk) {
     return B200BIT_OK;
 }
 
-/* path override for benchmarks/tests: 0 auto, 1 CUDA-core GEMV, 2 small-batch mma kernel, 3 general fallback;
+/* path override for benchmarks/tests: 0 auto, 1 CUDA-core GEMV, 2 small-batch mma kernel, 3 general fallback,
+ * 4 TMA-streamed small-batch kernel, 5 tcgen05 batched kernel, 6 cross-kernel pipelined decode GEMV;
  * mma_for_m1: in auto mode route M == 1 to the mma kernel (1) or to the CUDA-core GEMV (0) */
 int b200bit_set_path(int path, int mma_for_m1) {
-    B200_REQUIRE(path >= 0 && path <= 5, B200BIT_ERR_ARG, "path must be in [0,5]");
+    B200_REQUIRE(path >= 0 && path <= 6, B200BIT_ERR_ARG, "path must be in [0,6]");
     g_path = path;
     g_mma_for_m1 = mma_for_m1 ? 1 : 0;
     return B200BIT_OK;
@@ -533,6 +604,67 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
     if (M == 0) return B200BIT_OK;
 
     const bool trivial = (g_idx == nullptr);
+    // ---- decode (M == 1): cross-kernel pipelined CUDA-core GEMV ----
+    const PipePlan pp = (g_path == 6 || g_path == 0) ? plan_pipe(M, K, N, G, w_bit, asym, dtype, trivial) : PipePlan{};
+    if (pp.ok && !(g_path == 0 && g_mma_for_m1)) {
+        float* part = nullptr;
+        unsigned* tick = nullptr;
+        if (pp.splitk > 1) {
+            const size_t need = size_t(B200BIT_WS_TICKET_BYTES) + size_t(pp.splitk) * N * sizeof(float);
+            B200_REQUIRE(workspace && workspace_bytes >= need, B200BIT_ERR_WORKSPACE,
+                         "mpq_forward: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+            tick = reinterpret_cast<unsigned*>(workspace);
+            part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B200BIT_WS_TICKET_BYTES);
+        }
+        const bool bf16 = dtype == B200BIT_BF16;
+        CUtensorMap tw, ts, tz;
+        int rc = make_map_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_UINT32, qweight, uint64_t(N), uint64_t(K / nb), uint64_t(N) * 4,
+                             32, PG_STAGE_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        rc = make_map_2d(&ts, CU_TENSOR_MAP_DATA_TYPE_UINT16, scales, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
+                         uint32_t(pp.gps), CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        if (asym)
+            rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT32, zeros, uint64_t(N / nb), uint64_t(G),
+                             uint64_t(N / nb) * 4, uint32_t(32 / nb), uint32_t(pp.gps), CU_TENSOR_MAP_SWIZZLE_NONE);
+        else
+            rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT16, zeros, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
+                             uint32_t(pp.gps), CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        PipeParams p{};
+        p.x = reinterpret_cast<const uint16_t*>(x);
+        p.y = reinterpret_cast<uint16_t*>(y);
+        p.ws_part = part; p.tickets = tick;
+        p.K = K; p.N = N; p.R = K / nb;
+        p.stages_total = pp.stages_total; p.stages_per_split = pp.stages_per_split; p.S = pp.S;
+        p.rpg = pp.rpg; p.rpg_shift = pp.rpg_shift; p.sz_bytes = pp.sz_bytes;
+        p.s_tile_bytes = pp.s_tile_bytes; p.z_tile_bytes = pp.z_tile_bytes; p.asym = asym; p.trace = g_trace;
+        PipeLaunch l{};
+        l.FS = pp.FS; l.splitk = pp.splitk; l.strips = pp.strips; l.smem = pp.smem; l.flags = flags; l.stream = stream;
+        // 4-bit fp16 with >= 8 packed rows per group and the CTA's K range resident in the ring: 28-column strips,
+        // consumer math on the legacy tensor pipe, activations staged per warp (mpq_pipe_mma.cuh).  g_tune_L == 32
+        // keeps the CUDA-core FHFMA flavour for A/B measurements.
+        if (w_bit == 4 && !bf16 && pp.rpg % 8 == 0 && pp.stages_per_split <= pp.S && g_tune_L != 32) {
+            const int strips = (N + PGM_COLS - 1) / PGM_COLS;
+            B200_REQUIRE(size_t(strips) * sizeof(unsigned) <= B200BIT_WS_ZERO_OFFSET, B200BIT_ERR_SHAPE,
+                         "mpq_forward: N=%d too large for the ticket area", N);
+            rc = make_map_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_UINT32, qweight, uint64_t(N), uint64_t(K / nb), uint64_t(N) * 4,
+                             PGM_COLS, PG_STAGE_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc != B200BIT_OK) return rc;
+            if (asym) {     // packed zero rows: 8 words (64 nibbles) from word (28 * strip) >> 3 cover the strip
+                rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT32, zeros, uint64_t(N / nb), uint64_t(G),
+                                 uint64_t(N / nb) * 4, 8, uint32_t(pp.gps), CU_TENSOR_MAP_SWIZZLE_NONE);
+                if (rc != B200BIT_OK) return rc;
+                p.z_tile_bytes = pp.gps * 32;
+            }
+            l.FS = pp.rpg == 8 ? 1 : 2;
+            l.strips = strips;
+            l.smem = size_t(PGM_X_BYTES) + size_t(pp.S) * (PGM_TILE_BYTES + 2 * pp.sz_bytes) + PG_MAX_STAGES * 8 +
+                     PG_WARPS * 32 * 4 + 16;
+            return launch_pipe_mma(tw, ts, tz, p, l);
+        }
+        return launch_pipe(tw, ts, tz, p, l, w_bit, bf16);
+    }
     // ---- path selection: TMA-streamed tensor kernel (f16, M <= 32) > mma.sync kernel > CUDA-core GEMV > general ----
     // auto: M == 1 -> CUDA-core FHFMA GEMV (fastest measured at batch 1, profiles/r1_*); 2 <= M: TMA-streamed tensor kernel
     const UmmaPlan up = (g_path == 5) ? plan_umma(M, K, N, G, w_bit, asym, dtype, trivial) : UmmaPlan{};

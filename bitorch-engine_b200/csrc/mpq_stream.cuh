@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace b200bit {
 
@@ -46,55 +47,6 @@ struct StreamParams {
     unsigned long long* trace;   // optional [grid][16 warps][8] globaltimer stamps (diagnostics; nullptr = off)
 };
 
-// ---- mbarrier / TMA primitives (raw PTX) ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-
-// Uniform-datapath instructions (UTMALDG, UTCHMMA, UTCBAR) must be issued from CONVERGED code with only the instruction
-// itself predicated on an elected lane: inside a divergent region (`if (lane == 0)`, per-lane loops) the compiler wraps
-// every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop that costs ~100 cycles per instruction and serialises
-// the active lanes (measured: tools/umma_rate.cu, 114 -> 13 cycles per tcgen05.mma).
-__device__ __forceinline__ uint32_t um_elect() {
-    uint32_t leader;
-    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
-    return leader;
-}
-__device__ __forceinline__ void um_expect_tx(uint64_t* bar, unsigned bytes, uint32_t leader) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
-                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes), "r"(leader) : "memory");
-}
-__device__ __forceinline__ void um_tma_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint32_t leader) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
-                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "r"(leader) : "memory");
-}
-
-__device__ __forceinline__ unsigned long long st_gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 #define ST_TRACE(slot_) do { if (p.trace && lane == 0) p.trace[(size_t(blockIdx.x) * 16 + warp) * 8 + (slot_)] = st_gtime(); } while (0)
 
 __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
