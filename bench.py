@@ -178,8 +178,11 @@ def build_model(device, seed):
         for name, K, N in layer_shapes(LLAMA7B):
             qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (K * W_BIT // 32, N), dtype=torch.int32, device=device,
                                generator=g)
-            sc = (torch.rand((K // GROUP, N), device=device, generator=g) * 0.01 + 0.005).half()
-            zr = (sc.float() * 8 + torch.randn((K // GROUP, N), device=device, generator=g) * 1e-3).half()
+            # unit gain: uniform 4-bit codes have std 4.61, so std(w) = 1/sqrt(K) keeps rms(y) == rms(x) along the
+            # 160 chained layers of a token (activations stay O(1) in fp16); zero points centre the codes
+            s0 = 1.0 / (K ** 0.5 * 4.61)
+            sc = (s0 * (0.75 + 0.5 * torch.rand((K // GROUP, N), device=device, generator=g))).half()
+            zr = (sc.float() * 7.5).half()
             gi = (torch.arange(K, dtype=torch.int32, device=device) // GROUP)
             layers.append((name, K, N, qw, sc, zr, gi))
     return layers
@@ -239,14 +242,27 @@ def main():
     h, inter = LLAMA7B["hidden"], LLAMA7B["inter"]
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     x_h = torch.randn((1, h), device=dev, generator=g).half()
-    x_i = torch.randn((1, inter), device=dev, generator=g).half()
     pdl = bool(args.pdl)
 
     def token_pass():
-        y = None
-        for name, K, N, qw, sc, zr, gi in layers:
-            y = q_linear_cuda.mpq_forward(x_h if K == h else x_i, qw, sc, zr, gi, 16, W_BIT, False, pdl=pdl)
-        return y
+        """The decoder's dataflow between its linear layers (everything else -- attention, norms, SiLU -- is outside
+        this path and replaced by identity stand-ins): q, k, v read the hidden state; o reads v's output (stand-in for
+        the attention output); gate and up read o's output; down reads up's output; the next block reads down's."""
+        hid = x_h
+        per = len(layer_shapes(LLAMA7B))
+        for li in range(LLAMA7B["layers"]):
+            lq, lk, lv, lo, lg, lu, ld = layers[li * per:(li + 1) * per]
+
+            def fwd(x, layer):
+                name, K, N, qw, sc, zr, gi = layer
+                return q_linear_cuda.mpq_forward(x, qw, sc, zr, gi, 16, W_BIT, False, pdl=pdl)
+
+            q, k, v = fwd(hid, lq), fwd(hid, lk), fwd(hid, lv)      # all three stay alive, as attention needs them
+            o = fwd(v, lo)
+            gate, up = fwd(o, lg), fwd(o, lu)
+            hid = fwd(up, ld)
+            del q, k, gate
+        return hid
 
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
@@ -322,13 +338,15 @@ def main():
                 "config": {"workload": "llama7b_linear_layers_decode_bs1_w4_g128_sym", "layers_per_step": n_launch,
                            "weights_bytes": tok_bytes, "l2_policy": "inputs (3.4 GB of distinct weights per step) "
                            "larger than L2", "parallelism": f"replicas x{world}", "pdl": int(pdl),
+                           "dataflow": "llama decoder block: q,k,v <- hidden; o <- v (attention stand-in); "
+                                       "gate,up <- o; down <- up; next block <- down",
                            "tuning": tune or "heuristic", "cuda_graph": True},
                 "gpu_launches": n_launch * args.steps,
                 "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": x_host.numel() * 2,
                         "d2h_bytes_per_step": y_host.numel() * 2},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "mpq_pipe_kernel<4,f16,FS=4>", "avg_launch_us": per_launch_us,
+                             "kernel": "mpq_pipe_mma_kernel<FS2=2,sym> (4-bit f16 decode GEMV)", "avg_launch_us": per_launch_us,
                              "algorithmic_bytes_per_launch": tok_bytes / n_launch},
                 "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200bit.so")
 
 F32, F16, BF16, I8, I32 = 0, 1, 2, 3, 4
 FLAG_PDL = 1
+FLAG_INPUT_READY = 2
 WS_TICKET_BYTES = 16384
 
 _c_int, _c_size_t, _c_void_p, _c_uint = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_uint

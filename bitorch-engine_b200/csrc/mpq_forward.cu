@@ -12,6 +12,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 namespace b200bit {
 
@@ -49,6 +50,58 @@ static int g_path = 0;
 // in auto mode, does M == 1 go to the tensor kernel (1) or stay on the CUDA-core GEMV (0)?
 static int g_mma_for_m1 = 0;
 static unsigned long long* g_trace = nullptr;   // diagnostics: per-warp globaltimer stamps of the stream kernel
+
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic-dependent-launch chains (PipeParams::early).  Per (device, stream): the output ranges of the decode
+// kernels this library launched last -- one late-trigger kernel followed by the early ("sibling") kernels admitted
+// behind it.  A new launch may run early iff the caller promises that x is ready (B200BIT_FLAG_INPUT_READY), the
+// record is valid (the launch in front was a pipe kernel: every other kernel of the library triggers its dependents
+// before its own dependency wait) and x overlaps none of the recorded outputs.  Anything else starts a new chain.
+// Kernels launched by others between two calls do not trigger early, so they only make the order stricter.
+// ---------------------------------------------------------------------------------------------------------------
+struct ChainState {
+    int dev;
+    cudaStream_t stream;
+    bool used, valid;
+    int n;
+    uintptr_t lo[8], hi[8];
+    unsigned long long tick;
+};
+static ChainState g_chain[32];
+static std::mutex g_chain_mu;
+static unsigned long long g_chain_tick = 0;
+
+static ChainState* chain_entry(cudaStream_t stream) {      // caller holds g_chain_mu
+    int dev = 0;
+    cudaGetDevice(&dev);
+    ChainState* victim = &g_chain[0];
+    for (ChainState& e : g_chain) {
+        if (e.used && e.dev == dev && e.stream == stream) { e.tick = ++g_chain_tick; return &e; }
+        if (!e.used) { if (victim->used) victim = &e; }
+        else if (victim->used && e.tick < victim->tick) victim = &e;
+    }
+    *victim = ChainState{};
+    victim->used = true; victim->dev = dev; victim->stream = stream; victim->tick = ++g_chain_tick;
+    return victim;
+}
+static bool chain_admit(cudaStream_t stream, const void* x, size_t xbytes, const void* y, size_t ybytes, unsigned flags) {
+    static const bool enabled = !(getenv("B200BIT_EARLY") && atoi(getenv("B200BIT_EARLY")) == 0);
+    std::lock_guard<std::mutex> lk(g_chain_mu);
+    ChainState* e = chain_entry(stream);
+    const uintptr_t xl = reinterpret_cast<uintptr_t>(x), xh = xl + xbytes;
+    const uintptr_t yl = reinterpret_cast<uintptr_t>(y), yh = yl + ybytes;
+    bool early = enabled && (flags & B200BIT_FLAG_PDL) && (flags & B200BIT_FLAG_INPUT_READY) && e->valid && e->n < 8;
+    for (int i = 0; early && i < e->n; ++i)
+        if (xl < e->hi[i] && e->lo[i] < xh) early = false;
+    if (!early) e->n = 0;
+    e->lo[e->n] = yl; e->hi[e->n] = yh; ++e->n;
+    e->valid = true;
+    return early;
+}
+static void chain_invalidate(cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(g_chain_mu);
+    chain_entry(stream)->valid = false;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // General fallback: any g_idx (act-order), any dtype incl. f32, any N / group size.  One thread per column,
@@ -661,10 +714,16 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
             l.strips = strips;
             l.smem = size_t(PGM_X_BYTES) + size_t(pp.S) * (PGM_TILE_BYTES + 2 * pp.sz_bytes) + PG_MAX_STAGES * 8 +
                      PG_WARPS * 32 * 4 + 16;
-            return launch_pipe_mma(tw, ts, tz, p, l);
+            p.early = chain_admit(stream, x, size_t(K) * 2, y, size_t(N) * 2, flags) ? 1 : 0;
+            rc = launch_pipe_mma(tw, ts, tz, p, l);
+        } else {
+            p.early = chain_admit(stream, x, size_t(K) * 2, y, size_t(N) * 2, flags) ? 1 : 0;
+            rc = launch_pipe(tw, ts, tz, p, l, w_bit, bf16);
         }
-        return launch_pipe(tw, ts, tz, p, l, w_bit, bf16);
+        if (rc != B200BIT_OK) chain_invalidate(stream);
+        return rc;
     }
+    chain_invalidate(stream);      // every other kernel triggers its dependents before its own dependency wait
     // ---- path selection: TMA-streamed tensor kernel (f16, M <= 32) > mma.sync kernel > CUDA-core GEMV > general ----
     // auto: M == 1 -> CUDA-core FHFMA GEMV (fastest measured at batch 1, profiles/r1_*); 2 <= M: TMA-streamed tensor kernel
     const UmmaPlan up = (g_path == 5) ? plan_umma(M, K, N, G, w_bit, asym, dtype, trivial) : UmmaPlan{};

@@ -48,6 +48,15 @@ struct PipeParams {
     int sz_bytes;            // bytes reserved per stage for the scale tile (same again for the zero tile), 128-aligned
     int s_tile_bytes, z_tile_bytes;   // bytes the two TMA boxes deliver
     int asym;
+    // Programmatic-dependent-launch protocol (set by the host, mpq_forward.cu):
+    //   early == 0 (x may be produced by the kernel in front): prefetch weights, griddepcontrol.wait, THEN
+    //              launch_dependents, read x, compute, write y.  Triggering only after the wait guarantees that every
+    //              kernel in front of this one is complete and flushed when this kernel's dependents start.
+    //   early == 1 (x was complete before the previous b200bit kernel of this stream was launched -- a "sibling" such as
+    //              k_proj after q_proj): launch_dependents at once, read x and compute BEFORE griddepcontrol.wait
+    //              (overlapping the kernels in front), wait, then write y.  The final wait also keeps completion
+    //              transitive: this kernel cannot finish before the one in front of it.
+    int early;
     unsigned long long* trace;   // optional [grid][8] globaltimer stamps (diagnostics; nullptr = off)
 };
 
@@ -116,7 +125,7 @@ __global__ void __launch_bounds__(PG_THREADS, 3) mpq_pipe_kernel(const __grid_co
     if (tid < S) mbar_init(&full[tid], 1);
     else if (tid >= 32 && tid < 32 + S) mbar_init(&empty[tid - 32], PG_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    pdl_launch_dependents();
+    if (p.early) pdl_launch_dependents();     // see PipeParams::early
     __syncthreads();
 
     if (warp == PG_WARPS) {
@@ -134,11 +143,18 @@ __global__ void __launch_bounds__(PG_THREADS, 3) mpq_pipe_kernel(const __grid_co
             um_tma_2d(sz, &tm_s, strip * 32, g0, &full[s], leader);
             um_tma_2d(sz + p.sz_bytes, &tm_z, p.asym ? strip * (32 / NB) : strip * 32, g0, &full[s], leader);
             if (++s == S) { s = 0; ++round; }
+            if (!p.early && it == min(nst, S) - 1) {     // ring requested once: join the CTA's late trigger
+                pdl_wait_primary();
+                pdl_launch_dependents();
+            }
         }
     } else {
         // =========================== consumers ===========================
         const int cq = lane & 7, rl = lane >> 3;
-        pdl_wait_primary();          // x is produced by the previous kernel; y / workspace may still be in use by it
+        if (!p.early) {
+            pdl_wait_primary();      // x is produced by the previous kernel; y / workspace may still be in use by it
+            pdl_launch_dependents();
+        }
         PG_TRACE(1);
 
         const uint16_t* xg = p.x + size_t(r0) * NB;
@@ -243,6 +259,7 @@ __global__ void __launch_bounds__(PG_THREADS, 3) mpq_pipe_kernel(const __grid_co
     __syncthreads();
 
     // =========================== fixed-order CTA sum, output ===========================
+    if (p.early) pdl_wait_primary();          // y / workspace may still be in use by the previous kernel
     const int splitk = gridDim.y;
     const int n0 = strip * 32;
     if (tid < 32) {

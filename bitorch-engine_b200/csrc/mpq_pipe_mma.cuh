@@ -77,9 +77,16 @@ __global__ void __launch_bounds__(PGM_THREADS, 3) mpq_pipe_mma_kernel(const __gr
     const int units_cta = rows_cta / PG_UNIT_ROWS;
 
     PGM_TRACE(0);
+    if constexpr (TRACE) {      // slot 6 (the ticket stamp of split-K launches) carries the SM id otherwise
+        if (p.trace && tid == 0 && gridDim.y == 1) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.trace[size_t(blockIdx.x) * 8 + 6] = smid + 1;
+        }
+    }
     if (tid < S) mbar_init(&full[tid], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    pdl_launch_dependents();
+    if (p.early) pdl_launch_dependents();     // see PipeParams::early
     __syncthreads();
 
     if (warp == 0) {
@@ -102,7 +109,10 @@ __global__ void __launch_bounds__(PGM_THREADS, 3) mpq_pipe_mma_kernel(const __gr
     }
 
     const int g = lane >> 2, c = lane & 3;
-    pdl_wait_primary();          // x is produced by the previous kernel; y / workspace may still be in use by it
+    if (!p.early) {
+        pdl_wait_primary();      // x is produced by the previous kernel; y / workspace may still be in use by it
+        pdl_launch_dependents(); // only now: everything in front of this kernel is complete when its dependents start
+    }
     PGM_TRACE(1);
 
     // ---- this warp's activations: units it = 0..3 are packed rows it*128 + warp*16 + (0..15) of the CTA's K range.
@@ -227,6 +237,8 @@ __global__ void __launch_bounds__(PGM_THREADS, 3) mpq_pipe_mma_kernel(const __gr
     __syncthreads();
 
     // =========================== fixed-order CTA sum, output ===========================
+    if (p.early) pdl_wait_primary();          // y / workspace may still be in use by the previous kernel
+    PGM_TRACE(7);
     const int splitk = gridDim.y;
     const bool owner = tid < PGM_COLS && n0 + tid < p.N;
     if (owner) {

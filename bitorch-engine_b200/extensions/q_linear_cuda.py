@@ -29,6 +29,27 @@ def _gidx_is_trivial(g_idx, K, G):
     return verdict
 
 
+# (device index, stream) -> (x tensor of the previous decode call, its _version at that call).  The strong reference
+# keeps the storage alive, so an equal data_ptr() really is the same buffer and not a re-allocation.
+_prev_x = {}
+
+
+def _input_ready(x, stream):
+    """B200BIT_FLAG_INPUT_READY (include/b200bit.h): True when this call's activation is the very buffer the previous
+    mpq_forward call on this stream read (k_proj / v_proj after q_proj, up_proj after gate_proj) and torch has recorded
+    no in-place write to it since -- it was complete before that call, so this kernel may read it without waiting for
+    the kernels in front.  Writes torch does not version (a foreign kernel writing through data_ptr()) are the usual
+    caveat; B200BIT_EARLY=0 switches the overlap off."""
+    key = (x.device.index, stream)
+    prev = _prev_x.get(key)
+    _prev_x[key] = (x, x._version)
+    if prev is None:
+        return False
+    px, pv = prev
+    return (px.data_ptr() == x.data_ptr() and px.shape == x.shape and px.dtype == x.dtype and px._version == pv
+            and x._version == pv)
+
+
 def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False):
     """y[M,N] = x[M,K] @ dequant(qweight)  (q_linear_cuda.cpp:258-270 -> mpq_linear_cuda_kernel.cu:603-626).
 
@@ -62,11 +83,16 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         stream = torch.cuda.current_stream().cuda_stream
         need = lib.b200bit_mpq_forward_workspace_bytes(M, K, N, w_bit)
         ws = _cabi.workspace(x.device, stream, need)
+        flags = 0
+        if pdl:
+            flags = _cabi.FLAG_PDL
+            if M == 1 and _input_ready(x, stream):
+                flags |= _cabi.FLAG_INPUT_READY
         rc = lib.b200bit_mpq_forward(
             x.data_ptr(), qweight.data_ptr(), scales.data_ptr(), zeros.data_ptr(),
             None if trivial else g_idx.contiguous().data_ptr(), y.data_ptr(),
             M, K, N, G, w_bit, int(bool(asym)), _cabi.dtype_code(x.dtype),
-            ws.data_ptr(), ws.numel(), _cabi.FLAG_PDL if pdl else 0, stream)
+            ws.data_ptr(), ws.numel(), flags, stream)
     _cabi.check(rc)
     return y
 

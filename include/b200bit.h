@@ -57,6 +57,15 @@ extern "C" {
 
 /* flags for the `flags` argument of the forward entry points */
 #define B200BIT_FLAG_PDL 1u           /* launch with programmatic dependent launch (graph/stream overlap) */
+/* Caller's promise about x (decode GEMV, M == 1, with B200BIT_FLAG_PDL): x was completely written BEFORE the previous
+ * b200bit_mpq_forward launch on this stream was enqueued and has not been written since -- the "sibling" case of a
+ * decoder block (k_proj / v_proj after q_proj, up_proj after gate_proj: same hidden state).  The kernel then reads x
+ * and computes BEFORE griddepcontrol.wait, i.e. concurrently with the kernels in front of it, and only its output
+ * write waits for them.  The library honours the flag only when it knows that the launch in front on `stream` was one
+ * of its own late-trigger decode kernels (or a chain of such siblings) whose outputs do not overlap x; otherwise the
+ * call behaves exactly as without the flag.  No reference counterpart (the reference kernels run on the legacy
+ * default stream, fully serialised). */
+#define B200BIT_FLAG_INPUT_READY 2u
 
 B200BIT_API int b200bit_version(void);
 B200BIT_API const char* b200bit_last_error(void);
