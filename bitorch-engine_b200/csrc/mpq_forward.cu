@@ -9,6 +9,7 @@
 #include "mpq_umma.cuh"
 #include "mpq_pipe.cuh"
 #include "mpq_pipe_mma.cuh"
+#include "mpq_imma.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -45,7 +46,8 @@ int sm_count() {
 // process-wide tuning override for sweeps (0 = heuristic); set through b200bit_set_gemv_tuning()
 static int g_tune_L = 0, g_tune_warps = 0, g_tune_splitk = 0;
 // 0 = auto, 1 = CUDA-core FHFMA GEMV, 2 = mma.sync small-batch kernel, 3 = general fallback,
-// 4 = TMA-streamed small-batch kernel, 5 = tcgen05 batched kernel, 6 = cross-kernel pipelined decode GEMV (mpq_pipe.cuh)
+// 4 = TMA-streamed small-batch kernel, 5 = tcgen05 batched kernel, 6 = cross-kernel pipelined decode GEMV (mpq_pipe.cuh),
+// 7 = persistent integer-tensor-pipe decode GEMV (mpq_imma.cuh)
 static int g_path = 0;
 // in auto mode, does M == 1 go to the tensor kernel (1) or stay on the CUDA-core GEMV (0)?
 static int g_mma_for_m1 = 0;
@@ -566,6 +568,66 @@ static PipePlan plan_pipe(int M, int K, int N, int G, int w_bit, int asym, int d
     return pl;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// integer-tensor-pipe decode GEMV (mpq_imma.cuh): M == 1, 4-bit, f16 / bf16, contiguous groups
+// ---------------------------------------------------------------------------------------------------------------
+struct ImmaPlan {
+    bool ok;
+    int F, rpg, rpg_shift, gps, tiles, strips, n28, grid, S, sz_bytes, s_tile_bytes, z_tile_bytes;
+    size_t smem;
+};
+
+static ImmaPlan plan_imma(int M, int K, int N, int G, int w_bit, int asym, int dtype, bool trivial_gidx) {
+    ImmaPlan pl{};
+    pl.ok = false;
+    if (M != 1 || !trivial_gidx || w_bit != 4 || dtype == B200BIT_F32) return pl;
+    if (K % (8 * IM_UNIT_ROWS) != 0 || K % G != 0) return pl;
+    if (N % 8 != 0 || (asym && N % 32 != 0)) return pl;            // TMA row strides must be multiples of 16 bytes
+    const int gs = K / G;
+    if (gs % 32 != 0) return pl;
+    const int rpg = gs / 8;                                        // packed rows per group: 4, 8, 16, 32, ... (a power of two)
+    pl.rpg = rpg;
+    pl.rpg_shift = -1;
+    for (int sh = 2; sh <= 20; ++sh) if ((1 << sh) == rpg) pl.rpg_shift = sh;
+    if (pl.rpg_shift < 0) return pl;
+    pl.gps = rpg <= IM_TILE_ROWS ? IM_TILE_ROWS / rpg : 1;
+    pl.F = (rpg < IM_UNIT_ROWS ? rpg : IM_UNIT_ROWS) / 4;
+    pl.s_tile_bytes = pl.gps * 64;
+    pl.z_tile_bytes = asym ? pl.gps * 32 : pl.gps * 64;
+    pl.sz_bytes = (pl.s_tile_bytes + 127) & ~127;
+    const int R = K / 8;
+    pl.tiles = (R + IM_TILE_ROWS - 1) / IM_TILE_ROWS;
+    pl.strips = (N + IM_COLS - 1) / IM_COLS;
+    pl.n28 = pl.strips;
+    const int sms = sm_count();
+    pl.grid = 2 * pl.strips <= sms ? pl.strips : sms;      // a full wave whenever the layer has at least half a wave of strips
+    {
+        // even out the CTAs: round the strip count up to a multiple of the grid by making some strips 24 columns wide
+        // (the TMA box stays 28 wide, so each such strip fetches 4 columns twice) when that costs < 3 % extra traffic:
+        // 4096 columns -> 136 x 28 + 12 x 24 = 148 strips, exactly one per SM
+        const int want = (pl.strips + pl.grid - 1) / pl.grid * pl.grid;
+        const int n28 = (N - 24 * want) / 4;
+        if (want != pl.strips && N % 4 == 0 && n28 >= 0 && n28 <= want && (want - n28) * 4 * 100 < 3 * N) {
+            pl.strips = want;
+            pl.n28 = n28;
+        }
+        if (pl.grid > pl.strips) pl.grid = pl.strips;
+    }
+    const int T = ((pl.strips + pl.grid - 1) / pl.grid) * pl.tiles;   // most tiles any CTA walks
+    const size_t fixed = size_t(IM_XIMG_BYTES) + (2 * IM_WARPS * 32) * sizeof(float) + 2 * IM_MAX_STAGES * 8 + 64;
+    int S = g_tune_warps > 0 ? g_tune_warps : IM_MAX_STAGES;          // sweep hook: ring depth
+    if (S > IM_MAX_STAGES) S = IM_MAX_STAGES;
+    if (S > T) S = T;
+    for (; S >= 1; --S) {
+        pl.smem = fixed + size_t(S) * (IM_TILE_BYTES + 2 * pl.sz_bytes);
+        if (pl.smem <= size_t(IM_SMEM_LIMIT)) break;
+    }
+    if (S < 1) return pl;
+    pl.S = S;
+    pl.ok = true;
+    return pl;
+}
+
 static int launch_pipe(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tz, const PipeParams& p,
                        const PipeLaunch& l, int w_bit, bool bf16) {
     switch (w_bit) {
@@ -614,10 +676,11 @@ int b200bit_set_gemv_tuning(int L, int warps, int splitk) {
 }
 
 /* path override for benchmarks/tests: 0 auto, 1 CUDA-core GEMV, 2 small-batch mma kernel, 3 general fallback,
- * 4 TMA-streamed small-batch kernel, 5 tcgen05 batched kernel, 6 cross-kernel pipelined decode GEMV;
+ * 4 TMA-streamed small-batch kernel, 5 tcgen05 batched kernel, 6 cross-kernel pipelined decode GEMV (fp16-subnormal
+ * FHFMA / HMMA flavours), 7 persistent integer-tensor-pipe decode GEMV (4-bit);
  * mma_for_m1: in auto mode route M == 1 to the mma kernel (1) or to the CUDA-core GEMV (0) */
 int b200bit_set_path(int path, int mma_for_m1) {
-    B200_REQUIRE(path >= 0 && path <= 6, B200BIT_ERR_ARG, "path must be in [0,6]");
+    B200_REQUIRE(path >= 0 && path <= 7, B200BIT_ERR_ARG, "path must be in [0,7]");
     g_path = path;
     g_mma_for_m1 = mma_for_m1 ? 1 : 0;
     return B200BIT_OK;
@@ -657,6 +720,38 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
     if (M == 0) return B200BIT_OK;
 
     const bool trivial = (g_idx == nullptr);
+    // ---- decode (M == 1), 4-bit: persistent integer-tensor-pipe kernel (mpq_imma.cuh) ----
+    const ImmaPlan ip = (g_path == 7 || g_path == 0) ? plan_imma(M, K, N, G, w_bit, asym, dtype, trivial) : ImmaPlan{};
+    if (ip.ok && !(g_path == 0 && g_mma_for_m1)) {
+        CUtensorMap tw, ts, tz;
+        int rc = make_map_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_UINT32, qweight, uint64_t(N), uint64_t(K / 8), uint64_t(N) * 4,
+                             IM_COLS, IM_TILE_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        rc = make_map_2d(&ts, CU_TENSOR_MAP_DATA_TYPE_UINT16, scales, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
+                         uint32_t(ip.gps), CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        if (asym)       // packed zero rows: 8 words (64 nibbles) from word ((28 * strip) >> 3) & ~3 cover the strip
+            rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT32, zeros, uint64_t(N / 8), uint64_t(G), uint64_t(N / 8) * 4,
+                             8, uint32_t(ip.gps), CU_TENSOR_MAP_SWIZZLE_NONE);
+        else
+            rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT16, zeros, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
+                             uint32_t(ip.gps), CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != B200BIT_OK) return rc;
+        ImmaParams p{};
+        p.x = reinterpret_cast<const uint16_t*>(x);
+        p.y = reinterpret_cast<uint16_t*>(y);
+        p.K = K; p.N = N; p.R = K / 8; p.strips = ip.strips; p.n28 = ip.n28; p.tiles = ip.tiles; p.S = ip.S;
+        p.strips_q = ip.strips / ip.grid; p.strips_r = ip.strips % ip.grid;
+        p.rpg_shift = ip.rpg_shift; p.sz_bytes = ip.sz_bytes;
+        p.s_tile_bytes = ip.s_tile_bytes; p.z_tile_bytes = ip.z_tile_bytes; p.trace = g_trace;
+        ImmaLaunch l{};
+        l.F = ip.F; l.grid = ip.grid; l.asym = asym != 0; l.bf16 = dtype == B200BIT_BF16; l.smem = ip.smem;
+        l.flags = flags; l.stream = stream;
+        p.early = chain_admit(stream, x, size_t(K) * 2, y, size_t(N) * 2, flags) ? 1 : 0;
+        rc = launch_imma(tw, ts, tz, p, l);
+        if (rc != B200BIT_OK) chain_invalidate(stream);
+        return rc;
+    }
     // ---- decode (M == 1): cross-kernel pipelined CUDA-core GEMV ----
     const PipePlan pp = (g_path == 6 || g_path == 0) ? plan_pipe(M, K, N, G, w_bit, asym, dtype, trivial) : PipePlan{};
     if (pp.ok && !(g_path == 0 && g_mma_for_m1)) {

@@ -169,7 +169,8 @@ B200BIT_API int b200bit_binary_gemm(const uint8_t* x_bits, const uint8_t* w_bits
  * warps per CTA (1..16), split-K factor of the decode GEMV.  No reference counterpart. */
 B200BIT_API int b200bit_set_gemv_tuning(int lanes_per_row, int warps, int splitk);
 /* Kernel-path override (process-wide): 0 auto, 1 CUDA-core FHFMA GEMV, 2 small-batch mma.sync kernel, 3 general
- * fallback; mma_for_m1 selects, in auto mode, whether M == 1 uses the tensor kernel (1) or the CUDA-core GEMV (0). */
+ * fallback, 4 TMA-streamed small-batch kernel, 5 tcgen05 batched kernel, 6 pipelined decode GEMV (fp16-subnormal
+ * FHFMA / HMMA), 7 persistent integer-tensor-pipe decode GEMV (4-bit); mma_for_m1 selects, in auto mode, whether M == 1 uses the tensor kernel (1) or the CUDA-core GEMV (0). */
 B200BIT_API int b200bit_set_path(int path, int mma_for_m1);
 /* Diagnostics: device buffer of [grid][16][8] uint64 that receives %globaltimer stamps from the TMA-streamed kernel
  * (per CTA, per warp: start, init done, dependency wait done, first tile landed, first run done, all runs done,

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 CASES = load_nbit_cases()
 
 
-PATHS = {"auto": (0, 1), "gemv": (1, 0), "mma": (2, 1), "stream": (4, 1), "umma": (5, 1), "pipe": (6, 0)}
+PATHS = {"auto": (0, 0), "gemv": (1, 0), "mma": (2, 1), "stream": (4, 1), "umma": (5, 1), "pipe": (6, 0), "imma": (7, 0)}
 
 
 def _run(inp, w_bit, asym, path="auto"):
@@ -28,7 +28,7 @@ def _run(inp, w_bit, asym, path="auto"):
                                       asym)
         torch.cuda.synchronize()
     finally:
-        lib.b200bit_set_path(0, 1)
+        lib.b200bit_set_path(0, 0)
     return y
 
 
@@ -59,7 +59,7 @@ LLAMA = [(4096, 4096), (4096, 11008), (11008, 4096)]
 
 @pytest.mark.parametrize("K,N", LLAMA)
 @pytest.mark.parametrize("M", [1, 2, 4, 8, 32])
-@pytest.mark.parametrize("path", ["gemv", "mma", "stream", "umma", "pipe"])
+@pytest.mark.parametrize("path", ["auto", "gemv", "mma", "stream", "umma", "pipe", "imma"])
 def test_llama7b_shapes_4bit_g128(K, N, M, path):
     inp = make_mpq_inputs(K, N, 4, 128, "f16", False, M=M, seed=K + N + M, device="cuda")
     y = _run(inp, 4, False, path)
@@ -71,7 +71,7 @@ def test_llama7b_shapes_4bit_g128(K, N, M, path):
                                          (1, 32), (4, 1024)])
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
 @pytest.mark.parametrize("asym", [False, True])
-@pytest.mark.parametrize("path", ["gemv", "mma", "stream", "umma", "pipe"])
+@pytest.mark.parametrize("path", ["auto", "gemv", "mma", "stream", "umma", "pipe", "imma"])
 def test_bits_groups_dtypes(w_bit, group, dt, asym, path):
     K, N, M = 2048, 1024, 1
     inp = make_mpq_inputs(K, N, w_bit, group, dt, asym, M=M, seed=w_bit * 1000 + group, device="cuda")
@@ -128,7 +128,7 @@ def test_split_k_is_deterministic_and_tickets_reset():
                                        (8, 4, 16, "gemv"), (8, 4, 1, "mma"), (8, 8, 2, "mma"), (8, 2, 8, "mma"),
                                        (8, 1, 16, "mma"), (8, 0, 0, "stream"), (8, 7, 1, "stream"), (8, 12, 2, "stream"),
                                        (8, 5, 3, "stream"), (0, 0, 0, "pipe"), (0, 2, 1, "pipe"), (0, 0, 2, "pipe"), (0, 1, 4, "pipe"),
-                                       (0, 3, 3, "pipe")):
+                                       (0, 3, 3, "pipe"), (0, 0, 0, "imma"), (0, 1, 0, "imma"), (0, 2, 0, "imma")):
             assert lib.b200bit_set_gemv_tuning(L, warps, splitk) == 0
             ys = [_run(inp, 4, False, path) for _ in range(3)]
             assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])

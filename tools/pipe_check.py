@@ -11,7 +11,8 @@ from bitorch_engine_b200 import _cabi
 from bitorch_engine_b200.extensions import q_linear_cuda
 
 lib = _cabi.lib()
-lib.b200bit_set_path(6, 0)
+PATH = int(sys.argv[1]) if len(sys.argv) > 1 else 7      # 7: integer-tensor-pipe kernel, 6: fp16-subnormal pipe kernels
+lib.b200bit_set_path(PATH, 0)
 cases = [(256, 64, 4, 128, "f16", False, (0, 0, 0)), (4096, 4096, 4, 128, "f16", False, (0, 0, 0)),
          (4096, 11008, 4, 128, "f16", False, (0, 0, 0)), (11008, 4096, 4, 128, "f16", False, (0, 0, 0)),
          (11008, 4096, 4, 128, "f16", False, (0, 0, 1)), (11008, 4096, 4, 128, "f16", False, (0, 2, 2)),
@@ -26,7 +27,11 @@ cases = [(256, 64, 4, 128, "f16", False, (0, 0, 0)), (4096, 4096, 4, 128, "f16",
          (256, 64, 4, 128, "f16", False, (32, 0, 0)), (4096, 4096, 4, 128, "f16", False, (32, 0, 0)),
          (11008, 4096, 4, 128, "f16", True, (32, 0, 0)), (2048, 1024, 4, 64, "f16", True, (32, 0, 0)),
          (4096, 4096, 4, 128, "f16", True, (0, 0, 0)), (4096, 4096, 4, 128, "f16", False, (0, 0, 2)),
-         (2048, 1024, 4, 2048, "f16", False, (0, 0, 0))]
+         (2048, 1024, 4, 2048, "f16", False, (0, 0, 0)), (4096, 4096, 4, 32, "f16", False, (0, 0, 0)),
+         (4096, 4096, 4, 64, "bf16", True, (0, 0, 0)), (11008, 4096, 4, 128, "bf16", False, (0, 0, 0)),
+         (4096, 11008, 4, 128, "f16", True, (0, 0, 0)), (4096, 4096, 4, 4096, "f16", False, (0, 0, 0)),
+         (4096, 11008, 4, 128, "f16", False, (0, 1, 0)), (11008, 4096, 4, 128, "f16", False, (0, 2, 0)),
+         (8192, 1000, 4, 256, "f16", False, (0, 0, 0)), (14336, 4096, 4, 128, "f16", False, (0, 0, 0))]
 bad = 0
 for K, N, b, g, dt, asym, tune in cases:
     lib.b200bit_set_gemv_tuning(*tune)

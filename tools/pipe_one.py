@@ -8,7 +8,7 @@ from helpers import make_mpq_inputs
 from bitorch_engine_b200 import _cabi
 from bitorch_engine_b200.extensions import q_linear_cuda
 K, N = int(sys.argv[1]), int(sys.argv[2])
-lib = _cabi.lib(); lib.b200bit_set_path(6, 0)
+lib = _cabi.lib(); lib.b200bit_set_path(int(sys.argv[3]) if len(sys.argv) > 3 else 7, 0)
 inp = make_mpq_inputs(K, N, 4, 128, "f16", False, M=1, seed=1, device="cuda")
 y = q_linear_cuda.mpq_forward(inp["x"], inp["qweight"], inp["scales"], inp["zeros"], inp["g_idx"], 16, 4, False)
 torch.cuda.synchronize()

@@ -14,12 +14,13 @@ ap.add_argument("--pdl", type=int, default=1)
 ap.add_argument("--tune", default="0:0:0")
 ap.add_argument("--layers", type=int, default=3)
 ap.add_argument("--dataflow", default="llama")
+ap.add_argument("--path", type=int, default=7)
 ap.add_argument("--dump", default="", help="comma-separated node indices: per-CTA table (block, SM, stamps) of those nodes")
 ap.add_argument("--shapes", default="4096x4096,4096x4096,4096x4096,4096x4096,4096x11008,4096x11008,11008x4096")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 lib = _cabi.lib()
-lib.b200bit_set_path(6, 0)
+lib.b200bit_set_path(args.path, 0)
 L, wp, sk = (int(v) for v in args.tune.split(":"))
 lib.b200bit_set_gemv_tuning(L, wp, sk)
 g = torch.Generator(device=dev).manual_seed(0)
