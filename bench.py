@@ -346,7 +346,7 @@ def main():
                         "d2h_bytes_per_step": y_host.numel() * 2},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "mpq_pipe_mma_kernel<FS2=2,sym> (4-bit f16 decode GEMV)", "avg_launch_us": per_launch_us,
+                             "kernel": "mpq_imma_kernel<F=4,sym,f16> (4-bit decode GEMV, IMMA.16832.U8.S8)", "avg_launch_us": per_launch_us,
                              "algorithmic_bytes_per_launch": tok_bytes / n_launch},
                 "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:

@@ -86,8 +86,12 @@ static ChainState* chain_entry(cudaStream_t stream) {      // caller holds g_cha
     victim->used = true; victim->dev = dev; victim->stream = stream; victim->tick = ++g_chain_tick;
     return victim;
 }
-static bool chain_admit(cudaStream_t stream, const void* x, size_t xbytes, const void* y, size_t ybytes, unsigned flags) {
-    static const bool enabled = !(getenv("B200BIT_EARLY") && atoi(getenv("B200BIT_EARLY")) == 0);
+// B200BIT_EARLY: 0 = never run early, 1 = whenever the caller's promise and the record allow it (default),
+// 2 = only layers whose whole CTA range is resident in the ring before the wait (resident = true)
+static bool chain_admit(cudaStream_t stream, const void* x, size_t xbytes, const void* y, size_t ybytes, unsigned flags,
+                        bool resident = true) {
+    static const int mode = getenv("B200BIT_EARLY") ? atoi(getenv("B200BIT_EARLY")) : 1;
+    const bool enabled = mode == 1 || (mode == 2 && resident);
     std::lock_guard<std::mutex> lk(g_chain_mu);
     ChainState* e = chain_entry(stream);
     const uintptr_t xl = reinterpret_cast<uintptr_t>(x), xh = xl + xbytes;
@@ -614,7 +618,7 @@ static ImmaPlan plan_imma(int M, int K, int N, int G, int w_bit, int asym, int d
         if (pl.grid > pl.strips) pl.grid = pl.strips;
     }
     const int T = ((pl.strips + pl.grid - 1) / pl.grid) * pl.tiles;   // most tiles any CTA walks
-    const size_t fixed = size_t(IM_XIMG_BYTES) + (2 * IM_WARPS * 32) * sizeof(float) + 2 * IM_MAX_STAGES * 8 + 64;
+    const size_t fixed = size_t(IM_XIMG_BYTES) + (2 * IM_WARPS * 32) * sizeof(float) + IM_MAX_STAGES * 8 + IM_MAX_STAGES * 4 + 64;
     int S = g_tune_warps > 0 ? g_tune_warps : IM_MAX_STAGES;          // sweep hook: ring depth
     if (S > IM_MAX_STAGES) S = IM_MAX_STAGES;
     if (S > T) S = T;
@@ -747,7 +751,8 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
         ImmaLaunch l{};
         l.F = ip.F; l.grid = ip.grid; l.asym = asym != 0; l.bf16 = dtype == B200BIT_BF16; l.smem = ip.smem;
         l.flags = flags; l.stream = stream;
-        p.early = chain_admit(stream, x, size_t(K) * 2, y, size_t(N) * 2, flags) ? 1 : 0;
+        p.early = chain_admit(stream, x, size_t(K) * 2, y, size_t(N) * 2, flags,
+                              ((ip.strips + ip.grid - 1) / ip.grid) * ip.tiles <= ip.S) ? 1 : 0;
         rc = launch_imma(tw, ts, tz, p, l);
         if (rc != B200BIT_OK) chain_invalidate(stream);
         return rc;

@@ -23,15 +23,16 @@
 // 2^-15 of its unit's maximum loses low bits (absolute error <= 2^-27 of that maximum).
 //
 // Fragment mapping (m16n8k32, g = lane >> 2, c = lane & 3), 8-row block b of the warp's 16-row unit, k-step j in {0,1}:
-//   lane loads W = LDS.128 of packed row 8b + 2c + j, columns 4g .. 4g+3 of the strip (112-byte pitch: the eight lanes
-//   of a quarter warp touch eight different 16-byte bank groups)
-//   IMMA alpha: A row g <- column 4g: a0 = W.x UNMASKED (byte = 16 x code of k = 1,3,5,7 + code of k = 0,2,4,6),
-//               a2 = W.x & 0x0f0f0f0f (codes of k = 0,2,4,6); A row g+8 <- column 4g+1 (a1, a3 from W.y);
-//               IMMA beta: columns 4g+2, 4g+3 (W.z, W.w).  One LOP3 per packed word; the words are fetched as two LDS.64
-//               so that {raw, raw, masked, masked} is a register quad without moves.
+//   lane loads two LDS.64 of packed row 8b + 2c + j: columns 2g, 2g+1 (IMMA alpha) and 16+2g, 17+2g (IMMA beta) of the
+//   strip.  With the 112-byte pitch the sixteen lanes of a half warp (g = 0..3 or 4..7, c = 0..3) touch all 32 banks
+//   exactly once: shared memory moves every weight byte twice (TMA write + this read) and is the busiest unit of the SM.
+//   IMMA alpha: A row g <- column 2g: a0 = word UNMASKED (byte = 16 x code of k = 1,3,5,7 + code of k = 0,2,4,6),
+//               a2 = word & 0x0f0f0f0f (codes of k = 0,2,4,6); A row g+8 <- column 2g+1 (a1, a3).  One LOP3 per packed
+//               word, and {raw, raw, masked, masked} is a register quad without moves.
 //   B column (g & 3) = digit; with Xe = X[k even], Xo = X[k odd] / 16:  b0 = digit bytes of Xo, b1 = of (Xe - Xo), so
 //               (16 code_o + code_e) Xo + code_e (Xe - Xo) = 16 code_o Xo + code_e Xe: the unmasked low nibbles cancel
-//   D: lanes c = 0 hold digit columns 0,1, lanes c = 1 digit columns 2,3 (c = 2,3: duplicates, weight 0).
+//               Only lanes g < 4 load B (columns 4..7 of B are don't-care: their results are never read).
+//   D: lanes c = 0 hold digit columns 0,1, lanes c = 1 digit columns 2,3 (c = 2,3: don't-care columns, weight 0).
 // Replaces quant_mm_kernel{,_asym} (bitorch_engine/layers/qlinear/nbit/cuda/mpq_linear_cuda_kernel.cu:67-451) and the
 // torch::zeros memset in front of it (:618).
 #pragma once
@@ -89,6 +90,10 @@ __device__ __forceinline__ uint2 im_lds64(uint32_t a) {
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
     return r;
 }
+// B fragment: loaded by the lanes with p != 0 only, the others keep their (don't-care) registers
+__device__ __forceinline__ void im_lds64_if(uint2& r, uint32_t a, uint32_t p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0,%1}, [%2];\n\t}" : "+r"(r.x), "+r"(r.y) : "r"(a), "r"(p));
+}
 // ld.volatile: ptxas must not fuse two of these into one LDS.128 (the fused load forces register moves to build the
 // {raw, raw, masked, masked} A-fragment quads)
 __device__ __forceinline__ uint2 im_lds64v(uint32_t a) {
@@ -135,13 +140,13 @@ __global__ void __launch_bounds__(IM_THREADS, 2) mpq_imma_kernel(const __grid_co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = p.S;
     // carve-up: W ring S x 28672 | scale / zero tiles S x 2 x sz_bytes | per warp {x digit image [2 tiles][512 B],
-    //           xsum [2][4] f32, unit weight [2] f32} x 16 | red [2][16][32] f32 | mbarriers full[3], empty[3]
+    //           xsum [2][4] f32, unit weight [2] f32} x 16 | red [2][16][32] f32 | mbarriers full[3] | released[3] u32
     unsigned char* wst = im_smem;
     unsigned char* szst = wst + size_t(S) * IM_TILE_BYTES;
     unsigned char* ximg = szst + size_t(S) * 2 * p.sz_bytes;
     float* red = reinterpret_cast<float*>(ximg + IM_XIMG_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * IM_WARPS * 32);
-    uint64_t* empty = full + IM_MAX_STAGES;
+    unsigned* released = reinterpret_cast<unsigned*>(full + IM_MAX_STAGES);   // per slot: warps that are done with it (mod 16)
 
     // strips are dealt out cyclically (CTA b: b, b + grid, ...): at any moment the CTAs of a layer read ADJACENT strips,
     // i.e. together whole contiguous rows of the packed matrix.  Contiguous strip ranges per CTA leave two thirds of
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(IM_THREADS, 2) mpq_imma_kernel(const __grid_co
         }
     }
     if (tid < S) mbar_init(&full[tid], 1);
-    else if (tid >= 32 && tid < 32 + S) mbar_init(&empty[tid - 32], IM_WARPS);
+    else if (tid >= 32 && tid < 32 + S) released[tid - 32] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (p.early) pdl_launch_dependents();             // see PipeParams::early
     __syncthreads();
@@ -180,13 +185,15 @@ __global__ void __launch_bounds__(IM_THREADS, 2) mpq_imma_kernel(const __grid_co
         um_tma_2d(sz, &tm_s, n0 & ~7, g0, &full[slot], leader);
         um_tma_2d(sz + p.sz_bytes, &tm_z, ASYM ? ((n0 >> 3) & ~3) : (n0 & ~7), g0, &full[slot], leader);
     };
-    int rstrip = s_lo, rkt = 0;                       // next tile to request
-    if (warp == 0) {
+    // (rstrip, rkt) = tile that will be requested into the slot of the tile being consumed (S tiles ahead); every warp
+    // keeps the pair: the refill is issued by whichever warp releases a slot LAST, so no warp ever waits for the others
+    // (a fixed producer warp that first waited for all sixteen, then did its own unit, put its math on the critical path
+    // of every refill: 0.95 us per tile instead of 0.6, profiles/r57_timeline_imma.txt)
+    int rstrip = s_lo, rkt = 0;
+    for (int t = 0; t < S && t < T; ++t) {
         // ---- the first S tiles are requested BEFORE griddepcontrol.wait: weights do not depend on the previous kernel ----
-        for (int t = 0; t < S && t < T; ++t) {
-            issue_tile(rstrip, rkt, t);
-            if (++rkt == tiles) { rkt = 0; rstrip += s_step; }
-        }
+        if (warp == 0) issue_tile(rstrip, rkt, t);
+        if (++rkt == tiles) { rkt = 0; rstrip += s_step; }
     }
 
     const int g = lane >> 2, c = lane & 3;
@@ -265,29 +272,29 @@ __global__ void __launch_bounds__(IM_THREADS, 2) mpq_imma_kernel(const __grid_co
     // lane constants of the flush: digit-pair weight (c = 0: 1, c = 1: 65536, c >= 2: 0: duplicate digit columns)
     const float lane_w = (c == 0) ? 1.0f : (c == 1 ? 65536.0f : 0.0f);
     // shared-memory addresses of the hot loop as 32-bit offsets (no 64-bit pointer arithmetic in the loop)
-    const uint32_t w_base = smem_u32(wst) + uint32_t((warp * IM_UNIT_ROWS + (SEQ ? c : 2 * c)) * IM_PITCH + g * 16);
+    const uint32_t w_base = smem_u32(wst) + uint32_t((warp * IM_UNIT_ROWS + (SEQ ? c : 2 * c)) * IM_PITCH + g * 8);
     const uint32_t wp_base = smem_u32(ximg_w);                                      // warp-private region
     const uint32_t x_base = wp_base + uint32_t(c * 32 + (g & 3) * 8);
-    const uint32_t sz_base = smem_u32(szst) + uint32_t(g * 8);
-    const uint32_t full_base = smem_u32(full), empty_base = full_base + IM_MAX_STAGES * 8;
+    const uint32_t sz_base = smem_u32(szst) + uint32_t(g * 4);
+    const uint32_t zoff_lane = uint32_t(c < 2 ? 4 * g + 2 * c : 32 + 4 * g + 2 * (c - 2));   // column of this lane's zero-point term
+    const uint32_t x_loader = lane < 16 ? 1u : 0u;
+    uint2 xb = make_uint2(0u, 0u);
+    const uint32_t full_base = smem_u32(full);
     const uint32_t slot_sz = 2u * uint32_t(p.sz_bytes);
     const int unit_row = warp * IM_UNIT_ROWS;
+    // keep the lane's base addresses in registers: ptxas otherwise rebuilds them from %tid in every iteration
+    // (~25 of the ~140 instructions per unit)
+    uint32_t w_base_r = w_base, x_base_r = x_base, sz_base_r = sz_base, wp_base_r = wp_base;
+    asm volatile("" : "+r"(w_base_r), "+r"(x_base_r), "+r"(sz_base_r), "+r"(wp_base_r));
 
-    float yacc[4] = {0.f, 0.f, 0.f, 0.f};     // columns 4g .. 4g+3: sum of s * (x . q), this lane's digit pair
-    float yz = 0.f;                           // column 4g + c: sum of z * sum(x)
+    float yacc[4] = {0.f, 0.f, 0.f, 0.f};     // columns 2g, 2g+1, 16+2g, 17+2g: sum of s * (x . q), this lane's digit pair
+    float yz = 0.f;                           // column number c of those four: sum of z * sum(x)
     int strip = s_lo, kt = 0, slot = 0;
     unsigned ph = 0;
     bool out_waited = false;
     int rd_par = 0;
     int n0 = strip_col(strip);
     for (int t = 0; t < T; ++t) {
-        if (warp == 0 && t >= 1 && t - 1 + S < T) {
-            // refill the slot of the previous tile once all sixteen warps have released it
-            const int pslot = slot == 0 ? S - 1 : slot - 1;
-            im_mbar_wait(empty_base + pslot * 8, slot == 0 ? (ph ^ 1u) : ph);
-            issue_tile(rstrip, rkt, pslot);
-            if (++rkt == tiles) { rkt = 0; rstrip += s_step; }
-        }
         if ((kt & 1) == 0 && (passes > 1 || !staged_once)) {
             stage_x();                                 // tiles kt, kt + 1 of the strip
             staged_once = true;
@@ -297,17 +304,17 @@ __global__ void __launch_bounds__(IM_THREADS, 2) mpq_imma_kernel(const __grid_co
         if (kt * IM_TILE_ROWS + unit_row < p.R) {          // this warp's unit exists in the tile
             im_mbar_wait(full_base + slot * 8, ph);
             if (t == 0) IM_TRACE(3);
-            const uint32_t wt = w_base + uint32_t(slot) * IM_TILE_BYTES;
-            const uint32_t xt = x_base + uint32_t(kt & 1) * 512u;
-            const uint32_t sz = sz_base + uint32_t(slot) * slot_sz + uint32_t(n0 & 7) * 2u;   // strip starts at column n0 & 7 of the fp16 tile rows
-            const float wunit = __uint_as_float(im_lds32(wp_base + 1056u + uint32_t(kt & 1) * 4u)) * lane_w;
+            const uint32_t wt = w_base_r + uint32_t(slot) * IM_TILE_BYTES;
+            const uint32_t xt = x_base_r + uint32_t(kt & 1) * 512u;
+            const uint32_t sz = sz_base_r + uint32_t(slot) * slot_sz + uint32_t(n0 & 7) * 2u;   // strip starts at column n0 & 7 of the fp16 tile rows
+            const float wunit = __uint_as_float(im_lds32(wp_base_r + 1056u + uint32_t(kt & 1) * 4u)) * lane_w;
             int A[4], B[4];
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 const int b = ks >> 1, j = ks & 1;
                 const uint32_t wa_ = wt + uint32_t((b * 8 + (SEQ ? 4 * j : j)) * IM_PITCH);
-                const uint2 wa = im_lds64v(wa_), wb = im_lds64v(wa_ + 8u);
-                const uint2 xb = im_lds64(xt + uint32_t(b * 256 + j * 128));
+                const uint2 wa = im_lds64v(wa_), wb = im_lds64v(wa_ + 64u);
+                im_lds64_if(xb, xt + uint32_t(b * 256 + j * 128), x_loader);
                 if (ks % F == 0) {
                     im_mma_z(A, wa.x, wa.y, wa.x & 0x0f0f0f0fu, wa.y & 0x0f0f0f0fu, xb.x, xb.y);
                     im_mma_z(B, wb.x, wb.y, wb.x & 0x0f0f0f0fu, wb.y & 0x0f0f0f0fu, xb.x, xb.y);
@@ -319,37 +326,41 @@ __global__ void __launch_bounds__(IM_THREADS, 2) mpq_imma_kernel(const __grid_co
                     // ---- flush F k-steps (rows of one group) through the group's affine parameters ----
                     const int seg = ks / F;
                     const uint32_t gl = uint32_t((unit_row + seg * 4 * F) >> p.rpg_shift);    // group row inside the tile
-                    const float xs = __uint_as_float(im_lds32(wp_base + 1024u + uint32_t((kt & 1) * 16 + seg * 4)));
-                    const uint2 s4 = im_lds64(sz + gl * 64u);
-                    const uint32_t s2[2] = {s4.x, s4.y};
+                    const float xs = __uint_as_float(im_lds32(wp_base_r + 1024u + uint32_t((kt & 1) * 16 + seg * 4)));
+                    const uint32_t s2[2] = {im_lds32(sz + gl * 64u), im_lds32(sz + gl * 64u + 32u)};   // columns 2g, 2g+1 | 16+2g, 17+2g
                     float sq[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) sq[q] = (q & 1) ? cvt16_hi<BF16>(s2[q >> 1]) : cvt16_lo<BF16>(s2[q >> 1]);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {           // column 4g + q: IMMA alpha (q < 2) / beta, A row g (q even) / g + 8
+                    for (int q = 0; q < 4; ++q) {           // q = 0,1: columns 2g, 2g+1 (IMMA alpha rows g, g+8); q = 2,3: 16+2g, 17+2g (beta)
                         const int dlo = (q < 2) ? A[(q & 1) * 2] : B[(q & 1) * 2];
                         const int dhi = (q < 2) ? A[(q & 1) * 2 + 1] : B[(q & 1) * 2 + 1];
                         yacc[q] = fmaf(sq[q] * wunit, float(dhi * 256 + dlo), yacc[q]);
                     }
-                    // zero-point term of column 4g + c (one column per lane, combined with yacc at the end of the strip)
+                    // zero-point term of this lane's column q = c (one column per lane, combined with yacc at the end of the strip)
                     float zf;
                     if constexpr (ASYM) {
                         // zero tile row = 8 packed words from word (n0 >> 3) & ~3; the strip starts at nibble (n0 & 7) in {0, 4}
                         // of word (n0 >> 3) & 3 of the box
-                        const int gq = g + ((n0 & 7) >> 2);
+                        const int cz = int(zoff_lane >> 1) + (n0 & 7);          // nibble index inside the 64-nibble box row
                         const uint32_t zw = im_lds32(smem_u32(szst) + uint32_t(slot) * slot_sz + uint32_t(p.sz_bytes) + gl * 32u +
-                                                     uint32_t((((n0 >> 3) & 3) + (gq >> 1)) * 4));
+                                                     uint32_t((((n0 >> 3) & 3) + (cz >> 3)) * 4));
                         const float sc = c == 0 ? sq[0] : (c == 1 ? sq[1] : (c == 2 ? sq[2] : sq[3]));
-                        zf = sc * float(((zw >> ((gq & 1) * 16 + c * 4)) & 15u) + 1u);
+                        zf = sc * float(((zw >> ((cz & 7) * 4)) & 15u) + 1u);
                     } else {
-                        zf = cvt16_lo<BF16>(im_lds16(sz + uint32_t(p.sz_bytes) + gl * 64u + uint32_t(c * 2)));
+                        zf = cvt16_lo<BF16>(im_lds16(sz - uint32_t(g * 4) + uint32_t(p.sz_bytes) + gl * 64u + zoff_lane));
                     }
                     yz = fmaf(zf, xs, yz);
                 }
             }
         }
+        // ---- release the slot; the warp that releases it last requests tile t + S into it ----
         __syncwarp();
-        if (lane == 0) im_mbar_arrive(empty_base + slot * 8);
+        unsigned last = 0u;
+        if (lane == 0) last = ((atomicAdd(&released[slot], 1u) & unsigned(IM_WARPS - 1)) == unsigned(IM_WARPS - 1)) ? 1u : 0u;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last != 0u && t + S < T) issue_tile(rstrip, rkt, slot);
+        if (++rkt == tiles) { rkt = 0; rstrip += s_step; }
         if (++slot == S) { slot = 0; ph ^= 1u; }
         if (++kt == tiles) {
             if (t + 1 == T) IM_TRACE(4);
@@ -363,7 +374,10 @@ __global__ void __launch_bounds__(IM_THREADS, 2) mpq_imma_kernel(const __grid_co
             }
             float* rd = red + rd_par * (IM_WARPS * 32);
             rd_par ^= 1;
-            if (c == 0) *reinterpret_cast<float4*>(rd + warp * 32 + g * 4) = make_float4(yacc[0], yacc[1], yacc[2], yacc[3]);
+            if (c == 0) {
+                *reinterpret_cast<float2*>(rd + warp * 32 + 2 * g) = make_float2(yacc[0], yacc[1]);
+                *reinterpret_cast<float2*>(rd + warp * 32 + 16 + 2 * g) = make_float2(yacc[2], yacc[3]);
+            }
             yacc[0] = yacc[1] = yacc[2] = yacc[3] = 0.f;
             yz = 0.f;
             __syncthreads();
