@@ -120,6 +120,11 @@ __device__ __forceinline__ void im_mbar_wait(uint32_t bar, unsigned parity) {
         "bra IM_WAIT_LOOP;\n\t"
         "IM_WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ unsigned im_atoms_add(uint32_t a, unsigned v) {
+    unsigned r;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(a), "r"(v) : "memory");
+    return r;
+}
 __device__ __forceinline__ void im_mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -279,7 +284,8 @@ __global__ void __launch_bounds__(IM_THREADS, 2) mpq_imma_kernel(const __grid_co
     const uint32_t zoff_lane = uint32_t(c < 2 ? 4 * g + 2 * c : 32 + 4 * g + 2 * (c - 2));   // column of this lane's zero-point term
     const uint32_t x_loader = lane < 16 ? 1u : 0u;
     uint2 xb = make_uint2(0u, 0u);
-    const uint32_t full_base = smem_u32(full);
+    const uint32_t full_base = smem_u32(full), rel_base = smem_u32(released);
+    unsigned rel = 0u;
     const uint32_t slot_sz = 2u * uint32_t(p.sz_bytes);
     const int unit_row = warp * IM_UNIT_ROWS;
     // keep the lane's base addresses in registers: ptxas otherwise rebuilds them from %tid in every iteration
@@ -326,8 +332,26 @@ __global__ void __launch_bounds__(IM_THREADS, 2) mpq_imma_kernel(const __grid_co
                     // ---- flush F k-steps (rows of one group) through the group's affine parameters ----
                     const int seg = ks / F;
                     const uint32_t gl = uint32_t((unit_row + seg * 4 * F) >> p.rpg_shift);    // group row inside the tile
+                    // every shared-memory read of the segment first ...
                     const float xs = __uint_as_float(im_lds32(wp_base_r + 1024u + uint32_t((kt & 1) * 16 + seg * 4)));
                     const uint32_t s2[2] = {im_lds32(sz + gl * 64u), im_lds32(sz + gl * 64u + 32u)};   // columns 2g, 2g+1 | 16+2g, 17+2g
+                    uint32_t zraw;      // zero point of this lane's column q = c (one column per lane, combined with yacc at the end of the strip)
+                    int cz = 0;
+                    if constexpr (ASYM) {
+                        // zero tile row = 8 packed words from word (n0 >> 3) & ~3; the strip starts at nibble (n0 & 7) in {0, 4}
+                        // of word (n0 >> 3) & 3 of the box
+                        cz = int(zoff_lane >> 1) + (n0 & 7);                    // nibble index inside the 64-nibble box row
+                        zraw = im_lds32(smem_u32(szst) + uint32_t(slot) * slot_sz + uint32_t(p.sz_bytes) + gl * 32u +
+                                        uint32_t((((n0 >> 3) & 3) + (cz >> 3)) * 4));
+                    } else {
+                        zraw = im_lds16(sz - uint32_t(g * 4) + uint32_t(p.sz_bytes) + gl * 64u + zoff_lane);
+                    }
+                    if (ks == 3) {
+                        // ... then, after the unit's last read of the slot, release it: the atomic's round trip overlaps the
+                        // flush arithmetic below instead of sitting at the end of the unit
+                        __syncwarp();
+                        if (lane == 0) rel = im_atoms_add(rel_base + uint32_t(slot) * 4u, 1u);
+                    }
                     float sq[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) sq[q] = (q & 1) ? cvt16_hi<BF16>(s2[q >> 1]) : cvt16_lo<BF16>(s2[q >> 1]);
@@ -337,28 +361,22 @@ __global__ void __launch_bounds__(IM_THREADS, 2) mpq_imma_kernel(const __grid_co
                         const int dhi = (q < 2) ? A[(q & 1) * 2 + 1] : B[(q & 1) * 2 + 1];
                         yacc[q] = fmaf(sq[q] * wunit, float(dhi * 256 + dlo), yacc[q]);
                     }
-                    // zero-point term of this lane's column q = c (one column per lane, combined with yacc at the end of the strip)
                     float zf;
                     if constexpr (ASYM) {
-                        // zero tile row = 8 packed words from word (n0 >> 3) & ~3; the strip starts at nibble (n0 & 7) in {0, 4}
-                        // of word (n0 >> 3) & 3 of the box
-                        const int cz = int(zoff_lane >> 1) + (n0 & 7);          // nibble index inside the 64-nibble box row
-                        const uint32_t zw = im_lds32(smem_u32(szst) + uint32_t(slot) * slot_sz + uint32_t(p.sz_bytes) + gl * 32u +
-                                                     uint32_t((((n0 >> 3) & 3) + (cz >> 3)) * 4));
                         const float sc = c == 0 ? sq[0] : (c == 1 ? sq[1] : (c == 2 ? sq[2] : sq[3]));
-                        zf = sc * float(((zw >> ((cz & 7) * 4)) & 15u) + 1u);
+                        zf = sc * float(((zraw >> ((cz & 7) * 4)) & 15u) + 1u);
                     } else {
-                        zf = cvt16_lo<BF16>(im_lds16(sz - uint32_t(g * 4) + uint32_t(p.sz_bytes) + gl * 64u + zoff_lane));
+                        zf = cvt16_lo<BF16>(zraw);
                     }
                     yz = fmaf(zf, xs, yz);
                 }
             }
+        } else {
+            __syncwarp();
+            if (lane == 0) rel = im_atoms_add(rel_base + uint32_t(slot) * 4u, 1u);
         }
-        // ---- release the slot; the warp that releases it last requests tile t + S into it ----
-        __syncwarp();
-        unsigned last = 0u;
-        if (lane == 0) last = ((atomicAdd(&released[slot], 1u) & unsigned(IM_WARPS - 1)) == unsigned(IM_WARPS - 1)) ? 1u : 0u;
-        last = __shfl_sync(0xffffffffu, last, 0);
+        // ---- the warp that released the slot last requests tile t + S into it ----
+        const unsigned last = ((__shfl_sync(0xffffffffu, rel, 0) & unsigned(IM_WARPS - 1)) == unsigned(IM_WARPS - 1)) ? 1u : 0u;
         if (last != 0u && t + S < T) issue_tile(rstrip, rkt, slot);
         if (++rkt == tiles) { rkt = 0; rstrip += s_step; }
         if (++slot == S) { slot = 0; ph ^= 1u; }
