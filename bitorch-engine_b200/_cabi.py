@@ -94,6 +94,13 @@ def dtype_code(dtype):
     raise NotImplementedError(f"b200bit: tensor type not supported: {dtype}")
 
 
+def default_pdl():
+    """Inference-time default of the `pdl` argument of the forward shims (B200BIT_PDL=0 switches it off): launch with the
+    programmatic-dependent-launch attribute, so a layer's weight prefetch overlaps the kernel in front of it.  Training
+    keeps full stream serialisation (the optimizer rewrites the packed weights right in front of the next forward)."""
+    return os.environ.get("B200BIT_PDL", "1") != "0"
+
+
 _workspaces = {}
 
 

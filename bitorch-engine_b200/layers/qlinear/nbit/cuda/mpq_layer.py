@@ -8,6 +8,7 @@ import torch
 from torch.autograd import Function
 
 from .. import MPQLinearBase
+from ..... import _cabi
 from .....extensions import q_linear_cuda
 from .....utils.model_helper import flatten_x, unflatten_x
 
@@ -25,7 +26,8 @@ class MPQLinearCudaFunction(Function):
     @staticmethod
     def forward(ctx, x, qweight, a_bit, w_bit, scales, zeros, g_idx, asym, is_training, privileged_grad=None):
         x2, lead = flatten_x(x)
-        out = q_linear_cuda.mpq_forward(x2, qweight, scales, zeros, g_idx, a_bit, w_bit, asym)
+        out = q_linear_cuda.mpq_forward(x2, qweight, scales, zeros, g_idx, a_bit, w_bit, asym,
+                                        pdl=(not is_training) and _cabi.default_pdl())
         if is_training:
             qweight.privileged_grad = privileged_grad
             _stamp(qweight, scales, zeros, g_idx, w_bit, asym)

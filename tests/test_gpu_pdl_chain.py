@@ -131,3 +131,37 @@ def test_output_fed_back_as_input_waits():
             c2 = _fwd(b2, L["v"], 4, False, pdl=True)
             stream.synchronize()
             assert _same(a2, a) and _same(b2, b) and _same(c2, c)
+
+
+def test_module_forward_uses_pdl_at_inference_and_matches_serial(monkeypatch):
+    """MPQLinearCuda modules (requires_grad=False, the green-bit-llm inference configuration) launch with PDL by default
+    (B200BIT_PDL): q/k/v-style calls on one hidden state and a dependent call behind them give the serial results."""
+    from bitorch_engine_b200.layers.qlinear.nbit.cuda import MPQLinearCuda
+    torch.manual_seed(3)
+    mods = []
+    for i in range(4):
+        m = MPQLinearCuda(4096, 4096, w_bit=4, group_size=256, dq_group_size=256, use_gba_quant=True, requires_grad=False,
+                          dtype=torch.float16).cuda()
+        inp = make_mpq_inputs(4096, 4096, 4, 256, "f16", False, M=1, seed=200 + i, device="cuda")
+        m.qweight.data.copy_(inp["qweight"])
+        m.scales.data.copy_((inp["scales"].float() / (0.01 * 64 * 4.61)).half())
+        m.zeros.data.copy_((m.scales.float() * 7.5).half())
+        m.prepare_params()
+        m.eval()
+        mods.append(m)
+    x = torch.randn(1, 1, 4096, device="cuda").half()
+
+    def run():
+        with torch.no_grad():
+            q, k, v = mods[0](x), mods[1](x), mods[2](x)
+            o = mods[3](v)
+        torch.cuda.synchronize()
+        return [q, k, v, o]
+
+    monkeypatch.setenv("B200BIT_PDL", "0")
+    ref = run()
+    monkeypatch.setenv("B200BIT_PDL", "1")
+    for _ in range(5):
+        out = run()
+        for a, b in zip(out, ref):
+            assert a.shape == (1, 1, 4096) and _same(a, b)
