@@ -340,6 +340,9 @@ def main():
                            "larger than L2", "parallelism": f"replicas x{world}", "pdl": int(pdl),
                            "dataflow": "llama decoder block: q,k,v <- hidden; o <- v (attention stand-in); "
                                        "gate,up <- o; down <- up; next block <- down",
+                           "pdl_protocol": "dependent layers: wait, then trigger; layers that re-read the previous call's "
+                                           "input (k, v, up): compute before the wait (B200BIT_EARLY="
+                                           + os.environ.get("B200BIT_EARLY", "1") + ")",
                            "tuning": tune or "heuristic", "cuda_graph": True},
                 "gpu_launches": n_launch * args.steps,
                 "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": x_host.numel() * 2,
