@@ -37,6 +37,11 @@ PROTOTYPES = {
     "b200bit_binary_pack": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_void_p]),
     "b200bit_binary_relayout": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "b200bit_binary_gemm": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "b200bit_q4_pack": (_c_int, [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "b200bit_q4_unpack": (_c_int, [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "b200bit_q4_unpack_scale": (_c_int, [_c_void_p, ctypes.c_float, _c_void_p, _c_size_t, _c_void_p]),
+    "b200bit_sign_pack_u8": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "b200bit_sign_unpack_u8": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_size_t, _c_void_p]),
 }
 
 _lib = None

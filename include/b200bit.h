@@ -165,6 +165,26 @@ B200BIT_API int b200bit_binary_relayout(const uint8_t* in, uint8_t* out, int N, 
 B200BIT_API int b200bit_binary_gemm(const uint8_t* x_bits, const uint8_t* w_bits, void* out, int M, int N, int K,
                                     int stride_bytes, int out_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Wire-format conversions of the reference's `functions_cuda` extension (bitorch_engine/functions/cuda/
+ * functions_cuda.cpp:160-200; kernels functions_cuda_kernel.cu:74-209).  One-pass HBM streams.
+ *   b200bit_q4_pack         : int32 codes -> bytes, out[i] = (in[2i] & 15) << 4 | (in[2i+1] & 15)   (:136-159);
+ *                             n_bytes = number of OUTPUT bytes (= codes / 2)
+ *   b200bit_q4_unpack       : bytes -> int32 codes 0..15, high nibble first                       (:162-182)
+ *   b200bit_q4_unpack_scale : bytes -> f32, codes read as signed 4-bit (-8..7) times `scale`       (:185-209)
+ *   b200bit_sign_pack_u8    : eight values -> one byte, bit i = (v[8j+i] >= 0), LSB first; in_dtype F32 / F16 / BF16 /
+ *                             I8; n_bytes = number of OUTPUT bytes                                  (:74-119)
+ *   b200bit_sign_unpack_u8  : byte -> eight floats +-scale[byte_index / packed_dim], LSB first      (:123-133)
+ * `in` / `out` of the vectorised side must be 16-byte aligned (the shims clone unaligned views).
+ * fp32toint4 (:23-69, :239-262) is deliberately absent: the reference reads uninitialised shared memory there.
+ * ------------------------------------------------------------------------------------------------------------ */
+B200BIT_API int b200bit_q4_pack(const int32_t* in, int8_t* out, size_t n_bytes, void* stream);
+B200BIT_API int b200bit_q4_unpack(const int8_t* in, int32_t* out, size_t n_bytes, void* stream);
+B200BIT_API int b200bit_q4_unpack_scale(const int8_t* in, float scale, float* out, size_t n_bytes, void* stream);
+B200BIT_API int b200bit_sign_pack_u8(const void* in, int in_dtype, uint8_t* out, size_t n_bytes, void* stream);
+B200BIT_API int b200bit_sign_unpack_u8(const uint8_t* in, const float* scale, float* out, size_t n_bytes, size_t packed_dim,
+                                       void* stream);
+
 /* Sweep hook for bench.py / tests (process-wide; 0 = built-in heuristic): lanes per packed-row segment (8, 16, 32),
  * warps per CTA (1..16), split-K factor of the decode GEMV.  No reference counterpart. */
 B200BIT_API int b200bit_set_gemv_tuning(int lanes_per_row, int warps, int splitk);

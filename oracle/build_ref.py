@@ -2,13 +2,15 @@
 """TEST INFRASTRUCTURE ONLY -- compiles the UNMODIFIED reference extensions from the sources where they lie under
 /root/reference into oracle/_ref/ (git-ignored, shipped to the GPU box by gpurun).  Nothing is copied into the repo.
 
-    python oracle/build_ref.py [cpu] [binary_cuda] [q_linear_cuda]
+    python oracle/build_ref.py [cpu] [binary_cuda] [q_linear_cuda] [functions_cuda]
 
   binary_linear_cpp   (CPU, OpenMP)  bitorch_engine/layers/qlinear/binary/cpp/binary_linear.cpp
                       -> bit-exact oracle + CPU baseline for the binary path
   binary_linear_cuda  (sm_100a)      bitorch_engine/layers/qlinear/binary/cuda/{binary_linear_cuda.cpp,..._kernel.cu}
   q_linear_cuda       (sm_100a)      bitorch_engine/layers/qlinear/nbit/cuda/{q_linear_cuda.cpp, mpq_..., mbwq_...}.cu
                       -> the reference CUDA path, run on the GPU box as the secondary oracle and as the kernel-to-beat
+  functions_cuda      (sm_100a)      bitorch_engine/functions/cuda/{functions_cuda.cpp, functions_cuda_kernel.cu}
+                      -> bit-exact oracle of the q4 / sign-bit wire formats on the GPU box
 The reference's own build helper is bypassed on purpose (it appends -ccbin=/usr/bin/gcc-11, which does not exist here;
 bitorch_engine/utils/cuda_extension.py:94-97)."""
 import os
@@ -52,6 +54,10 @@ def build_ref(what=("cpu",)):
         mods["q_linear_cuda"] = _load("q_linear_cuda",
                                       [f"{d}/q_linear_cuda.cpp", f"{d}/mpq_linear_cuda_kernel.cu",
                                        f"{d}/mbwq_linear_cuda_kernel.cu"], cuda=True, extra_include=[f"{d}/exl2"])
+    if "functions_cuda" in what:
+        d = f"{REF}/functions/cuda"
+        mods["functions_cuda"] = _load("functions_cuda", [f"{d}/functions_cuda.cpp", f"{d}/functions_cuda_kernel.cu"],
+                                       cuda=True)
     return mods
 
 
