@@ -20,7 +20,13 @@ def test_reference_module_paths_resolve():
             "assert all(hasattr(m, n) for n in ['mpq_forward','mpq_grad_input','mbwq_trans_qweight','mbwq_q42fp_weight',"
             "'mbwq_q4_forward','mbwq_exl2fp_weight','mbwq_exl2_forward']);"
             "b = importlib.import_module('bitorch_engine.extensions.binary_linear_cuda');"
-            "assert all(hasattr(b, n) for n in ['forward','w_pack','mm']); print('ok')")
+            "assert all(hasattr(b, n) for n in ['forward','w_pack','mm']);"
+            "f = importlib.import_module('bitorch_engine.extensions.functions_cuda');"
+            "assert all(hasattr(f, n) for n in ['fp32toint4','tensor_pack_to_uint8','uint8_to_unpacked_tensor','q4_pack',"
+            "'q4_unpack','q4_unpack_and_scaling']);"
+            "from bitorch_engine.functions.cuda import q4_pack_tensor, q4_unpack_tensor, q4_unpack_and_scaling_tensor;"
+            "from bitorch_engine.functions.cuda.functions import tensor_to_packed_uint8, unpack_uint8_tensor;"
+            "print('ok')")
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "compat"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
