@@ -24,6 +24,7 @@ PROTOTYPES = {
     "b200bit_set_gemv_tuning": (_c_int, [_c_int, _c_int, _c_int]),
     "b200bit_set_path": (_c_int, [_c_int, _c_int]),
     "b200bit_set_trace_buffer": (_c_int, [_c_void_p]),
+    "b200bit_mpq_decode_plan": (_c_int, [_c_int] * 6 + [ctypes.POINTER(_c_int)]),
     "b200bit_mpq_forward_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
     "b200bit_mpq_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                      _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

@@ -670,6 +670,16 @@ int b200bit_device_info(int* sm, int* major, int* minor) {
     return B200BIT_OK;
 }
 
+/* host-side plan of the 4-bit decode kernel for a shape (no launch, no device needed) */
+int b200bit_mpq_decode_plan(int K, int N, int G, int w_bit, int asym, int dtype, int* out8) {
+    B200_REQUIRE(out8 != nullptr, B200BIT_ERR_ARG, "mpq_decode_plan: null output pointer");
+    B200_REQUIRE(K > 0 && N > 0 && G > 0, B200BIT_ERR_SHAPE, "mpq_decode_plan: bad sizes K=%d N=%d G=%d", K, N, G);
+    const ImmaPlan pl = plan_imma(1, K, N, G, w_bit, asym, dtype, true);
+    const int vals[8] = {pl.ok ? 1 : 0, pl.grid, pl.strips, pl.n28, pl.tiles, pl.S, pl.F, int(pl.smem)};
+    for (int i = 0; i < 8; ++i) out8[i] = pl.ok ? vals[i] : (i == 0 ? 0 : 0);
+    return B200BIT_OK;
+}
+
 /* sweep hook (bench / tests only): lanes per row segment (8/16/32), warps per CTA, split-K; 0 = heuristic */
 int b200bit_set_gemv_tuning(int L, int warps, int splitk) {
     B200_REQUIRE(L == 0 || L == 8 || L == 16 || L == 32, B200BIT_ERR_ARG, "L must be 0, 8, 16 or 32");

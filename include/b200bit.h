@@ -185,6 +185,11 @@ B200BIT_API int b200bit_sign_pack_u8(const void* in, int in_dtype, uint8_t* out,
 B200BIT_API int b200bit_sign_unpack_u8(const uint8_t* in, const float* scale, float* out, size_t n_bytes, size_t packed_dim,
                                        void* stream);
 
+/* Host-side plan of the 4-bit decode kernel (mpq_imma.cuh) for a layer shape, without launching anything (tests of the
+ * host logic; needs no device: the SM count falls back to 148).  out8 receives {ok, grid, strips, strips_28_wide,
+ * tiles_per_strip, ring_slots, k_steps_per_flush, shared_memory_bytes}; returns 0, or B200BIT_ERR_ARG for a null pointer. */
+B200BIT_API int b200bit_mpq_decode_plan(int K, int N, int G, int w_bit, int asym, int dtype, int* out8);
+
 /* Sweep hook for bench.py / tests (process-wide; 0 = built-in heuristic): lanes per packed-row segment (8, 16, 32),
  * warps per CTA (1..16), split-K factor of the decode GEMV.  No reference counterpart. */
 B200BIT_API int b200bit_set_gemv_tuning(int lanes_per_row, int warps, int splitk);
