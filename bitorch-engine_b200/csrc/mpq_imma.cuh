@@ -6,14 +6,16 @@
 //     (mpq_pipe.cuh: FHFMA, mpq_pipe_mma.cuh: HMMA.16816) spend ~224 issue slots per 4096 weights (4 LOP3 + 1 SHF per
 //     packed word just to isolate the nibbles, 256 weights per HMMA): 40 - 52 GB/s per SM, i.e. the whole GPU computes
 //     at about the speed HBM delivers, so compute cannot hide behind the weight stream and the chain is 2x HBM time.
-//     A packed word ANDed with 0x0f0f0f0f / 0xf0f0f0f0 is already a valid u8 A-fragment register (codes 0..15, and
-//     16 x codes for the odd nibbles): 2 LOP3 per word, 512 weights per IMMA, and IMMA.16832 issues at the same
+//     A packed word is already a valid u8 A-fragment register -- as it is (byte = 16 x odd code + even code) and ANDed
+//     with 0x0f0f0f0f (byte = even code): 1 LOP3 per word, 512 weights per IMMA, and IMMA.16832 issues at the same
 //     0.5 / clk / SM as HMMA.16816 (tools/microbench4.cu) -- half the tensor time and a third of the issue slots.
 //   * CTAs of one layer that land on the same SM finish 1.5x later than the median (r51_timeline_dump.txt: 52 of the
-//     147 CTAs of a 4096x4096 layer shared an SM while 27 SMs had none).  grid = min(#strips, #SMs) persistent CTAs of
-//     512 threads, two resident per SM (the layer computing + the next one prefetching): every SM always has exactly
-//     one free slot when the next layer launches, so placement stays one CTA per layer per SM.  No split-K, no
-//     tickets, no workspace: a CTA walks whole 28-column strips through a TMA ring and writes y once.
+//     147 CTAs of a 4096x4096 layer shared an SM while 27 SMs had none).  grid = #SMs persistent CTAs of 512 threads
+//     (4096 columns = 136 strips of 28 + 12 of 24 = 148), two resident per SM (the layer computing + the next one
+//     prefetching): every SM always has exactly one free slot when the next layer launches, so placement stays one
+//     CTA per layer per SM.  No split-K, no tickets, no workspace: a CTA walks whole 28-column strips (dealt out
+//     cyclically, so that the CTAs of a layer read whole contiguous rows together) through a 3-slot TMA ring, refilled
+//     by whichever warp releases a slot last, and writes y once.
 //
 // Exactness.  x (f16 / bf16) of a 128-value unit is scaled by a power of two to a 31-bit fixed-point integer X
 // (odd k: 27 bits, the odd nibbles carry a factor 16) and split into four balanced base-256 digits in [-128, 127];
