@@ -53,3 +53,29 @@ def test_input_ready_inference():
     y = torch.zeros((1, 64), dtype=torch.float16)
     assert q._input_ready(y, 7) is False                   # a different buffer
     assert q._input_ready(x, 7) is False                   # ... and back: not the immediately preceding input
+
+
+def test_shims_reject_host_tensors_like_the_reference():
+    """CHECK_CUDA of the reference (q_linear_cuda.cpp:255-256, functions_cuda.cpp) -> RuntimeError, before any library call."""
+    import pytest
+    from bitorch_engine_b200.extensions import q_linear_cuda, functions_cuda, binary_linear_cuda
+    x = torch.zeros((1, 256), dtype=torch.float16)
+    qw = torch.zeros((32, 64), dtype=torch.int32)
+    sc = torch.ones((2, 64), dtype=torch.float16)
+    with pytest.raises(RuntimeError):
+        q_linear_cuda.mpq_forward(x, qw, sc, sc, None, 16, 4, False)
+    with pytest.raises(RuntimeError):
+        functions_cuda.q4_pack(torch.zeros((2, 2), dtype=torch.int32), False)
+    with pytest.raises(RuntimeError):
+        functions_cuda.tensor_pack_to_uint8(torch.zeros((2, 8)))
+    with pytest.raises(NotImplementedError):
+        functions_cuda.fp32toint4(torch.zeros(64))
+    assert hasattr(binary_linear_cuda, "forward") and hasattr(binary_linear_cuda, "w_pack")
+
+
+def test_default_pdl_switch(monkeypatch):
+    from bitorch_engine_b200 import _cabi
+    monkeypatch.delenv("B200BIT_PDL", raising=False)
+    assert _cabi.default_pdl() is True
+    monkeypatch.setenv("B200BIT_PDL", "0")
+    assert _cabi.default_pdl() is False
