@@ -23,3 +23,63 @@ def prepare_bie_layers(model: torch.nn.Module, layers=None) -> None:
         fn = getattr(module, "prepare_params", None)
         if callable(fn) and module is not model:
             fn()
+
+
+def pad_embedding_dim(weight: torch.Tensor) -> torch.Tensor:
+    """Pad the embedding dimension (dim 1) with -1 columns up to the next multiple of 8, the unit of the sign-bit
+    packing (model_helper.py:54-82).  -1 packs to bit 0, so the padding never flips a popcount."""
+    extra = -weight.shape[1] % 8
+    if extra == 0:
+        return weight
+    fill = torch.full((weight.shape[0], extra), -1.0, dtype=torch.float, device=weight.device)
+    return torch.cat([weight, fill], dim=1)
+
+
+def pad_last_2_dims_to_multiple_of_128(tensor: torch.Tensor):
+    """Zero-pad the last two dimensions up to multiples of 128 (the BTC tile of the binary matmul); returns the padded
+    tensor and the number of rows added to the second-to-last dimension (model_helper.py:85-117)."""
+    pad_last = -tensor.shape[-1] % 128
+    pad_sec = -tensor.shape[-2] % 128
+    if pad_last or pad_sec:
+        tensor = torch.nn.functional.pad(tensor, (0, pad_last, 0, pad_sec), mode="constant", value=0)
+    return tensor, pad_sec
+
+
+def binary_matmul_forward_post_processing(tensor: torch.Tensor, shape_pre: list, x_pad_sec_last: int,
+                                          y_pad_sec_last: int, k: int) -> torch.Tensor:
+    """Undo the padding of a batched binary matmul result [b, m, n], restore the leading shape and map popcounts back
+    to the +-1 domain: k - 2 * popc (model_helper.py:120-155)."""
+    if x_pad_sec_last > 0:
+        tensor = tensor[:, :-x_pad_sec_last, :]
+    if y_pad_sec_last > 0:
+        tensor = tensor[:, :, :-y_pad_sec_last]
+    tensor = tensor.reshape(list(shape_pre) + [tensor.size(-2), tensor.size(-1)])
+    return k - 2 * tensor
+
+
+def _quantised_layer_bases():
+    from ..layers.qlinear.binary import BinaryLinearBase
+    from ..layers.qlinear.nbit import MPQLinearBase
+    return [BinaryLinearBase, MPQLinearBase]
+
+
+def pack_bie_layers(model: torch.nn.Module, qweight_only: bool = True, layers=None) -> None:
+    """Call generate_quantized_weight(qweight_only) on every quantised sub-module (model_helper.py:199-235): the step in
+    front of torch.save.  The default layer list holds the bases this package provides (binary and MPQ Linear)."""
+    layers = tuple(layers) if layers else tuple(_quantised_layer_bases())
+    for idx, module in enumerate(model.modules()):
+        if idx > 0 and isinstance(module, layers):
+            module.generate_quantized_weight(qweight_only=qweight_only)
+
+
+def save_checkpoint(model: torch.nn.Module, name: str, qweight_only: bool = True) -> None:
+    """Pack, then torch.save({'state_dict': ...}) (model_helper.py:238-263)."""
+    pack_bie_layers(model, qweight_only)
+    torch.save({"state_dict": model.state_dict()}, name)
+
+
+def load_checkpoint(model: torch.nn.Module, checkpoint_path: str, qweight_only: bool = True) -> None:
+    """Pack (so that the packed buffers exist), then load the state dict non-strictly (model_helper.py:266-283)."""
+    pack_bie_layers(model, qweight_only)
+    checkpoint = torch.load(checkpoint_path)
+    model.load_state_dict(checkpoint["state_dict"], strict=False)

@@ -43,3 +43,70 @@ def init_weight(weight: torch.Tensor, cls: Type[torch.nn.Parameter] = torch.nn.P
     q = nv_tensor_quant(centred)[0]
     q = torch.where(q == 0, centred.sign(), q)
     return cls(q.to(torch.int8)), scale_w
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bit-packing specifications in plain Python and activation quantisers (quant_operators.py:93-307, 348-368).  Host-side
+# helpers either side of the kernels: the packers are the written-down format of the CPU binary layer's words, the
+# q8 / q4 quantisers are the activation side of the W4A4 / W8A8 layers, the zero-point packer is the inverse of what the
+# fused optimizer kernel unpacks.
+# ---------------------------------------------------------------------------------------------------------------
+def bit_set(var: int, pos: int, val: int) -> int:
+    """var | (val << pos)   (quant_operators.py:93-115)."""
+    return var | (val << pos)
+
+
+def get_binary_row(nd_row, binary_row, nd_size: int, bits_per_binary_word: int):
+    """Sign-bit words of a flat row-major array: word w, bit j = (nd_row[w * bits + j] >= 0), LSB first
+    (quant_operators.py:118-173)."""
+    for w in range(0, nd_size, bits_per_binary_word):
+        word = 0
+        for j in range(bits_per_binary_word):
+            word = bit_set(word, j, 1 if nd_row[w + j] >= 0 else 0)
+        binary_row[w // bits_per_binary_word] = word
+    return binary_row
+
+
+def get_binary_col(nd_col, binary_col, dim_n: int, dim_k: int, bits_per_binary_word: int):
+    """Sign-bit words down the columns of a flat [dim_n, dim_k] array: word (y, x), bit b = (nd_col[(y * bits + b) * dim_k
+    + x] >= 0)   (quant_operators.py:176-231)."""
+    for y in range(dim_n // bits_per_binary_word):
+        for x in range(dim_k):
+            word = 0
+            for b in range(bits_per_binary_word):
+                word = bit_set(word, b, 1 if nd_col[(y * bits_per_binary_word + b) * dim_k + x] >= 0 else 0)
+            binary_col[y * dim_k + x] = word
+    return binary_col
+
+
+def _uniform_quant(input: torch.Tensor, scale_a, eps, default_divisor: float, lo: int, hi: int):
+    scale_given = scale_a is not None
+    x = input if input.dtype == torch.float else input.to(torch.float)
+    if scale_a is None:
+        scale_a = 2 * x.abs().mean() / default_divisor
+    if eps is None:
+        eps = torch.tensor(0.00001, dtype=x.dtype, device=x.device)
+    scale_a = torch.where(scale_a > eps, scale_a, eps)
+    q = (x / scale_a).round().clamp(lo, hi)
+    return q if scale_given else (q, scale_a)
+
+
+def q8_quantization(input: torch.Tensor, scale_a: torch.Tensor = None, eps: torch.Tensor = None):
+    """round(x / max(scale, eps)) clamped to [-128, 127]; scale defaults to 2 * mean|x| / 11.269 and is then returned
+    as well (quant_operators.py:234-269).  (The reference's own default for `eps` calls `.device(...)` on a tensor and
+    raises; a float32 1e-5 on the input's device is used here.)"""
+    return _uniform_quant(input, scale_a, eps, 11.269, -128, 127)
+
+
+def q4_quantization(input: torch.Tensor, scale_a: torch.Tensor = None, eps: torch.Tensor = None):
+    """4-bit twin: clamp to [-8, 7], default scale 2 * mean|x| / 5.6345 (quant_operators.py:272-307)."""
+    return _uniform_quant(input, scale_a, eps, 5.6345, -8, 7)
+
+
+def gptq_style_zeros_packing(zeros: torch.Tensor, w_bit: int, out_features: int, group_size: int) -> torch.Tensor:
+    """Integer zero points [G, N] (value = stored field + 1) -> packed int32 [G, N * w_bit / 32], LSB first
+    (quant_operators.py:348-368)."""
+    per = 32 // w_bit
+    z = (zeros.reshape(zeros.shape[0], out_features // 32 * w_bit, per).to(torch.int32) - 1) & ((1 << w_bit) - 1)
+    shifts = torch.arange(0, 32, w_bit, device=zeros.device, dtype=torch.int32)
+    return torch.bitwise_left_shift(z, shifts.view(1, 1, -1)).sum(dim=-1).to(torch.int32)

@@ -210,6 +210,48 @@ def gen_layers():
     print(f"layers: {len(specs)} configs -> tests/golden/layer_specs.json, layer_prepare.npz")
 
 
+
+
+def gen_helpers():
+    """Host-side helpers either side of the path, by the reference's own Python (CPU): utils/model_helper.py
+    pad_embedding_dim (54-82), pad_last_2_dims_to_multiple_of_128 (85-117), binary_matmul_forward_post_processing
+    (120-155); utils/quant_operators.py get_binary_row / get_binary_col (118-231), q8_quantization / q4_quantization
+    (234-307), gptq_style_zeros_packing (348-368).  -> tests/golden/helper_cases.npz"""
+    from bitorch_engine.utils import model_helper as mh
+    from bitorch_engine.utils import quant_operators as qo
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    w = torch.randn((5, 13), generator=g)
+    out["pad_emb_in"], out["pad_emb_out"] = w.numpy(), mh.pad_embedding_dim(w).numpy()
+    w8 = torch.randn((3, 16), generator=g)
+    out["pad_emb8_in"], out["pad_emb8_out"] = w8.numpy(), mh.pad_embedding_dim(w8).numpy()
+    t = torch.randn((2, 100, 130), generator=g)
+    p, sec = mh.pad_last_2_dims_to_multiple_of_128(t)
+    out["pad128_in"], out["pad128_out"], out["pad128_sec"] = t.numpy(), p.numpy(), np.array(sec)
+    bm = torch.randint(0, 64, (2, 128, 128), generator=g).float()
+    out["bmm_in"] = bm.numpy()
+    out["bmm_out"] = mh.binary_matmul_forward_post_processing(bm, [2], 30, 28, 64).numpy()
+    x = torch.randn((4, 64), generator=g)
+    x[0, :3] = torch.tensor([0.0, -0.0, -1e-9])
+    row = qo.get_binary_row(x.flatten().tolist(), [0] * (x.numel() // 32), x.numel(), 32)
+    out["bin_in"], out["bin_row"] = x.numpy(), np.array(row, dtype=np.uint64)
+    col = qo.get_binary_col(x.t().contiguous().flatten().tolist(), [0] * (64 // 32 * 4), 64, 4, 32)
+    out["bin_col"] = np.array(col, dtype=np.uint64)
+    a = torch.randn((7, 33), generator=g) * 3
+    q8, s8 = qo.q8_quantization(a, eps=torch.tensor(1e-5))
+    q4, s4 = qo.q4_quantization(a, eps=torch.tensor(1e-5))
+    out["q_in"], out["q8"], out["q8_scale"], out["q4"], out["q4_scale"] = a.numpy(), q8.numpy(), s8.numpy(), q4.numpy(), s4.numpy()
+    sc = torch.tensor(0.37)
+    out["q8_given"] = qo.q8_quantization(a, sc, torch.tensor(1e-5)).numpy()
+    out["q4_given"] = qo.q4_quantization(a, sc, torch.tensor(1e-5)).numpy()
+    for b in (2, 4, 8):
+        z = torch.randint(1, 2 ** b + 1, (4, 64), generator=g)
+        out[f"zp{b}_in"] = z.numpy()
+        out[f"zp{b}_out"] = qo.gptq_style_zeros_packing(z, b, 64, 32).numpy()
+    np.savez_compressed(os.path.join(GOLD, "helper_cases.npz"), **out)
+    print("helper_cases.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["nbit"]
     for w in what:

@@ -15,7 +15,8 @@ def test_reference_module_paths_resolve():
             "from bitorch_engine.layers.qlinear.nbit import MPQWeightParameter;"
             "from bitorch_engine.layers.qlinear.binary.cuda import BinaryLinearCuda, BMM;"
             "from bitorch_engine.optim import DiodeMix;"
-            "from bitorch_engine.utils.model_helper import flatten_x, prepare_bie_layers;"
+            "from bitorch_engine.utils.model_helper import flatten_x, prepare_bie_layers, save_checkpoint, load_checkpoint, pad_embedding_dim;"
+            "from bitorch_engine.utils.quant_operators import q4_quantization, q8_quantization, get_binary_row, gptq_style_zeros_packing;"
             "m = importlib.import_module('bitorch_engine.extensions.q_linear_cuda');"
             "assert all(hasattr(m, n) for n in ['mpq_forward','mpq_grad_input','mbwq_trans_qweight','mbwq_q42fp_weight',"
             "'mbwq_q4_forward','mbwq_exl2fp_weight','mbwq_exl2_forward']);"
