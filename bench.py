@@ -196,6 +196,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("B200BIT_PDL", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chain", type=int, default=int(os.environ.get("B200BIT_CHAIN", "1")),
+                    help="1: the token's 224 layer calls recorded into ONE decode-chain launch (DecodeChain.capture); "
+                         "0: one launch per layer (programmatic dependent launch), as in round 1")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -267,14 +270,26 @@ def main():
         return hid
 
     stream = torch.cuda.Stream(device=dev)
+    use_chain = bool(args.chain)
     with torch.cuda.stream(stream):
         token_pass()                      # eager warm-up: g_idx verdict cache, workspace, module load
         stream.synchronize()
+        if use_chain:
+            # the same 224 plugin calls, recorded instead of launched: one persistent kernel runs the token
+            from bitorch_engine_b200.decode_chain import DecodeChain
+            chain = DecodeChain.capture(token_pass)
+            y_out = chain.outputs
+            chain.launch()
+            chain.check()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
-            y_out = token_pass()
+            if use_chain:
+                chain.launch()
+            else:
+                y_out = token_pass()
     torch.cuda.synchronize()
-    n_launch = len(layers)
+    n_layers = len(layers)
+    n_launch = 1 if use_chain else n_layers
 
     def barrier():
         if world > 1:
@@ -334,24 +349,32 @@ def main():
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        if use_chain:
+            chain.check()
+            kernel = ("mpq_chain_kernel<F=4,sym,f16> (224 4-bit decode GEMVs in one persistent launch, IMMA.16832.U8.S8, "
+                      "TMA ring across layer boundaries)")
+            protocol = "decode chain: device-side dependency counters, weight ring refilled across layer boundaries"
+        else:
+            kernel = "mpq_imma_kernel<F=4,sym,f16> (4-bit decode GEMV, IMMA.16832.U8.S8)"
+            protocol = ("dependent layers: wait, then trigger; layers that re-read the previous call's input (k, v, up): "
+                        "compute before the wait (B200BIT_EARLY=" + os.environ.get("B200BIT_EARLY", "1") + ")")
         line = {"metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                "config": {"workload": "llama7b_linear_layers_decode_bs1_w4_g128_sym", "layers_per_step": n_launch,
+                "config": {"workload": "llama7b_linear_layers_decode_bs1_w4_g128_sym", "layers_per_step": n_layers,
+                           "launches_per_step": n_launch, "decode_chain": int(use_chain),
                            "weights_bytes": tok_bytes, "l2_policy": "inputs (3.4 GB of distinct weights per step) "
                            "larger than L2", "parallelism": f"replicas x{world}", "pdl": int(pdl),
                            "dataflow": "llama decoder block: q,k,v <- hidden; o <- v (attention stand-in); "
                                        "gate,up <- o; down <- up; next block <- down",
-                           "pdl_protocol": "dependent layers: wait, then trigger; layers that re-read the previous call's "
-                                           "input (k, v, up): compute before the wait (B200BIT_EARLY="
-                                           + os.environ.get("B200BIT_EARLY", "1") + ")",
+                           "pdl_protocol": protocol,
                            "tuning": tune or "heuristic", "cuda_graph": True},
                 "gpu_launches": n_launch * args.steps,
                 "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": x_host.numel() * 2,
                         "d2h_bytes_per_step": y_host.numel() * 2},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "mpq_imma_kernel<F=4,sym,f16> (4-bit decode GEMV, IMMA.16832.U8.S8)", "avg_launch_us": per_launch_us,
+                             "kernel": kernel, "avg_launch_us": per_launch_us,
                              "algorithmic_bytes_per_launch": tok_bytes / n_launch},
                 "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:

@@ -29,6 +29,11 @@ PROTOTYPES = {
     "b200bit_mpq_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                      _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                      _c_void_p, _c_size_t, _c_uint, _c_void_p]),
+    "b200bit_mpq_chain_plan_bytes": (_c_size_t, [_c_void_p, _c_int]),
+    "b200bit_mpq_chain_build": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_size_t,
+                                         ctypes.POINTER(_c_int)]),
+    "b200bit_mpq_chain_launch": (_c_int, [_c_void_p, ctypes.POINTER(_c_int), _c_uint, _c_void_p]),
+    "b200bit_mpq_chain_status": (_c_int, [_c_void_p, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), _c_void_p]),
     "b200bit_mpq_grad_input": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p]),
     "b200bit_mpq_dequant": (_c_int, [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p, _c_void_p]),
     "b200bit_exl2_dequant": (_c_int, [_c_void_p] * 6 + [_c_int, _c_int, ctypes.POINTER(_c_int), _c_void_p]),
@@ -44,6 +49,14 @@ PROTOTYPES = {
     "b200bit_sign_pack_u8": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "b200bit_sign_unpack_u8": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_size_t, _c_void_p]),
 }
+
+
+
+class ChainNode(ctypes.Structure):
+    """b200bit_chain_node (include/b200bit.h)."""
+    _fields_ = [("x", _c_void_p), ("y", _c_void_p), ("qweight", _c_void_p), ("scales", _c_void_p), ("zeros", _c_void_p),
+                ("K", _c_int), ("N", _c_int), ("G", _c_int), ("reserved", _c_int)]
+
 
 _lib = None
 _lock = threading.Lock()

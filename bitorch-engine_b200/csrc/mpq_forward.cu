@@ -52,6 +52,7 @@ static int g_path = 0;
 // in auto mode, does M == 1 go to the tensor kernel (1) or stay on the CUDA-core GEMV (0)?
 static int g_mma_for_m1 = 0;
 static unsigned long long* g_trace = nullptr;   // diagnostics: per-warp globaltimer stamps of the stream kernel
+unsigned long long* trace_buffer() { return g_trace; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Programmatic-dependent-launch chains (PipeParams::early).  Per (device, stream): the output ranges of the decode
@@ -376,7 +377,7 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static int make_map_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+int make_map_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
                        uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
     EncodeTiledFn fn = get_encode_fn();
     B200_REQUIRE(fn != nullptr, B200BIT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");

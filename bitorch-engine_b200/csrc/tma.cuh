@@ -5,6 +5,10 @@
 
 namespace b200bit {
 
+// host: cuTensorMapEncodeTiled through the driver entry point (mpq_forward.cu); 2-D, no interleave, 256-byte L2 promotion
+int make_map_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw);
+
 // ---- mbarrier / TMA primitives (raw PTX) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {

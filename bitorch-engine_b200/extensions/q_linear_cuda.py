@@ -72,6 +72,13 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         raise ValueError(f"scales dtype {scales.dtype} must match x dtype {x.dtype}")
     if M == 0:
         return torch.empty((0, N), dtype=x.dtype, device=x.device)
+    from .. import decode_chain
+    rec = decode_chain.recording()
+    if rec is not None:
+        # DecodeChain.capture: the call becomes a node of the chain (nothing is launched here)
+        if not _gidx_is_trivial(g_idx, K, G):
+            raise NotImplementedError("DecodeChain: act-order g_idx is not supported inside a chain")
+        return rec.add(x, qweight, scales, zeros, w_bit, asym)
     x = x.contiguous()
     qweight = qweight.contiguous()
     scales = scales.contiguous()

@@ -89,6 +89,38 @@ B200BIT_API int b200bit_mpq_forward(const void* x, const int32_t* qweight, const
                         void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Decode chain: ONE persistent launch runs a list of batch-1 (M == 1) 4-bit Linear layers whose dataflow is given by
+ * their pointers (node j reads what node i < j wrote when the ranges overlap).  Same arithmetic and bit-identical
+ * results as b200bit_mpq_forward at M == 1; the weight stream is prefetched across layer boundaries and dependent layers
+ * synchronise on the device -- through the data itself ({values, launch epoch} words) or through counters -- instead of
+ * kernel boundaries (csrc/mpq_chain.cuh).  Use it for consecutive
+ * Linear layers with nothing else between them: fused q/k/v and gate/up segments of a decoder block, or the whole
+ * linear-layer chain of a token.  Replaces n x mpq_forward (q_linear_cuda.cpp:258-270 -> mpq_linear_cuda_kernel.cu:603-626).
+ *   b200bit_mpq_chain_plan_bytes : size of the caller-owned device buffer that holds the plan (128-byte aligned)
+ *   b200bit_mpq_chain_build      : host array of nodes -> plan image in plan_device (synchronous copy; call it once, outside
+ *                                  graph capture) + info16 (16 host ints the caller keeps and hands to launch)
+ *   b200bit_mpq_chain_launch     : enqueue the chain on `stream` (graph-capturable; launches of ONE plan must be
+ *                                  stream-ordered; cooperative launch: the device must be able to hold grid = #SMs CTAs)
+ *   b200bit_mpq_chain_status     : 0 / 1 = a dependency wait inside the kernel gave up (synchronises the stream)
+ * Constraints: w_bit 4, f16 / bf16, contiguous groups of 32 * 2^i values (one group size per chain), K % 128 == 0,
+ * N % 8 == 0 (asym: N % 32 == 0), no node may write its own input.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    const void* x;            /* [K] activations (dtype of the chain) */
+    void* y;                  /* [N] output */
+    const int32_t* qweight;   /* int32 [K/8, N] */
+    const void* scales;       /* [G, N] */
+    const void* zeros;        /* sym: [G, N]; asym: packed int32 [G, N/8] */
+    int K, N, G;
+    int reserved;
+} b200bit_chain_node;
+B200BIT_API size_t b200bit_mpq_chain_plan_bytes(const b200bit_chain_node* nodes_host, int n_nodes);
+B200BIT_API int b200bit_mpq_chain_build(const b200bit_chain_node* nodes_host, int n_nodes, int w_bit, int asym, int dtype,
+                                        void* plan_device, size_t plan_bytes, int* info16_host);
+B200BIT_API int b200bit_mpq_chain_launch(void* plan_device, const int* info16_host, unsigned flags, void* stream);
+B200BIT_API int b200bit_mpq_chain_status(const void* plan_device, const int* info16_host, int* error_flag_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * MPQ grad_input:  dx[M,K] = dy[M,N] @ W^T  (same dequantisation as the forward; fp32 accumulation; deterministic).
  * Replaces q_linear_cuda.mpq_grad_input (q_linear_cuda.cpp:272-284 -> mpq_linear_cuda_kernel.cu:1198-1223,
  * back_quant_mm_kernel{,_asym} :635-1049).  Argument meaning as b200bit_mpq_forward.
