@@ -37,12 +37,14 @@ PROTOTYPES = {
     "b200bit_mpq_grad_input": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p]),
     "b200bit_mpq_dequant": (_c_int, [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p, _c_void_p]),
     "b200bit_exl2_dequant": (_c_int, [_c_void_p] * 6 + [_c_int, _c_int, ctypes.POINTER(_c_int), _c_void_p]),
-    "b200bit_mpq_pack_weight": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p]),
+    "b200bit_mpq_pack_weight": (_c_int, [_c_void_p] * 6 + [_c_int] * 8 + [_c_void_p]),
     "b200bit_diodemix_mpq_step": (_c_int, [_c_void_p] * 6 + [_c_int] * 8 + [ctypes.c_double] * 4 + [_c_int, _c_void_p]),
     "b200bit_diodemix_binary_step": (_c_int, [_c_void_p] * 5 + [_c_size_t, _c_int] + [ctypes.c_double] * 3 + [_c_void_p]),
     "b200bit_binary_pack": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_void_p]),
     "b200bit_binary_relayout": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "b200bit_binary_gemm": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "b200bit_cpu_binary_pack": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int]),
+    "b200bit_cpu_binary_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int]),
     "b200bit_q4_pack": (_c_int, [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "b200bit_q4_unpack": (_c_int, [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "b200bit_q4_unpack_scale": (_c_int, [_c_void_p, ctypes.c_float, _c_void_p, _c_size_t, _c_void_p]),

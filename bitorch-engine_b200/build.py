@@ -23,14 +23,14 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_m
 
 
 def _sources():
-    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    return sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
 
 
 def _deps_hash():
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for f in sorted(os.listdir(root)):
-            if f.endswith((".cu", ".cuh", ".inl", ".h")):
+            if f.endswith((".cu", ".cuh", ".inl", ".h", ".cpp")):
                 with open(os.path.join(root, f), "rb") as fh:
                     h.update(f.encode())
                     h.update(fh.read())
@@ -51,7 +51,7 @@ def build_lib(force=False, verbose=False):
         flags += ["-Xptxas", "-v"]
 
     def compile_one(src):
-        obj = os.path.join(OBJ, src[:-3] + ".o")
+        obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         cmd = [NVCC] + ARCH + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r

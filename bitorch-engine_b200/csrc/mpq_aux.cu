@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(256) mpq_dequant_kernel(const uint32_t* __rest
 // the `unpacked_zeros` argument of pack_fp_weight).  perm (int16 [K], nullable) gathers rows: w[perm[k], n]
 // (utils.py:124-126, MBWQ q_perm).
 // ---------------------------------------------------------------------------------------------------------------
-template <int DT>
+// WT = dtype of `weight` (the optimizer hands over an fp32 weight next to half scales: torch then promotes, i.e. every op
+// of the expression is evaluated -- and rounded -- in fp32)
+template <int DT, int WT>
 __global__ void __launch_bounds__(256) mpq_pack_kernel(const void* __restrict__ weight, const void* __restrict__ scales,
                                                        const void* __restrict__ zeros, const int32_t* __restrict__ g_idx,
                                                        const int16_t* __restrict__ perm, uint32_t* __restrict__ out, int K,
@@ -114,10 +116,11 @@ __global__ void __launch_bounds__(256) mpq_pack_kernel(const void* __restrict__ 
             g_prev = g;
         }
         const int ks = perm ? int(uint16_t(perm[k])) : k;
-        const float wv = El<DT>::ld(weight, size_t(ks) * N + n);
+        constexpr int CT = (WT == B200BIT_F32) ? B200BIT_F32 : DT;       // torch's type promotion
+        const float wv = El<WT>::ld(weight, size_t(ks) * N + n);
         float t;
-        if (asym) t = El<DT>::rnd(__fadd_rn(El<DT>::rnd(__fdiv_rn(wv, s)), z));
-        else t = El<DT>::rnd(__fdiv_rn(El<DT>::rnd(__fadd_rn(wv, z)), s));
+        if (asym) t = El<CT>::rnd(__fadd_rn(El<CT>::rnd(__fdiv_rn(wv, s)), z));
+        else t = El<CT>::rnd(__fdiv_rn(El<CT>::rnd(__fadd_rn(wv, z)), s));
         float c = rintf(t);
         c = fminf(fmaxf(c, 0.f), maxq);
         if (!(c == c)) c = 0.f;   // NaN -> 0 (torch: undefined conversion; keep the word well-formed)
@@ -312,17 +315,22 @@ int b200bit_exl2_dequant(const int32_t* qweight, const void* scales, const void*
 
 int b200bit_mpq_pack_weight(const void* weight, const void* scales, const void* zeros, const int32_t* g_idx,
                             const int16_t* perm, int32_t* qweight_out, int K, int N, int G, int w_bit, int asym,
-                            int zeros_unpacked, int dtype, void* stream_) {
+                            int zeros_unpacked, int dtype, int weight_dtype, void* stream_) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+    B200_REQUIRE(weight_dtype == dtype || weight_dtype == B200BIT_F32, B200BIT_ERR_UNSUPPORTED,
+                 "mpq_pack_weight: weight dtype code %d with parameter dtype code %d (same dtype, or an fp32 weight)", weight_dtype, dtype);
     int rc = check_common("mpq_pack_weight", weight, scales, zeros, qweight_out, K, N, G, w_bit, asym, dtype);
     if (rc != B200BIT_OK) return rc;
     B200_REQUIRE(g_idx || K % G == 0, B200BIT_ERR_SHAPE, "mpq_pack_weight: K=%d not divisible by G=%d", K, G);
     const int nb = 32 / w_bit;
     dim3 grid((N + 255) / 256, K / nb);
     uint32_t* o = reinterpret_cast<uint32_t*>(qweight_out);
-    if (dtype == B200BIT_F32) mpq_pack_kernel<B200BIT_F32><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);
-    else if (dtype == B200BIT_F16) mpq_pack_kernel<B200BIT_F16><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);
-    else mpq_pack_kernel<B200BIT_BF16><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);
+    const bool wf32 = weight_dtype == B200BIT_F32;
+    if (dtype == B200BIT_F32) mpq_pack_kernel<B200BIT_F32, B200BIT_F32><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);
+    else if (dtype == B200BIT_F16 && wf32) mpq_pack_kernel<B200BIT_F16, B200BIT_F32><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);
+    else if (dtype == B200BIT_F16) mpq_pack_kernel<B200BIT_F16, B200BIT_F16><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);
+    else if (wf32) mpq_pack_kernel<B200BIT_BF16, B200BIT_F32><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);
+    else mpq_pack_kernel<B200BIT_BF16, B200BIT_BF16><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);
     B200_CUDA_OK(cudaGetLastError());
     return B200BIT_OK;
 }

@@ -1,6 +1,7 @@
 // mpq_chain.cu -- host side of the decode chain (mpq_chain.cuh): hazard analysis, plan image, launch, C ABI.
 #include "mpq_chain.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -91,6 +92,7 @@ int b200bit_mpq_chain_build(const b200bit_chain_node* nodes, int n, int w_bit, i
                  chain_plan_bytes(nodes, n), plan_bytes);
     B200_REQUIRE((reinterpret_cast<uintptr_t>(plan_device) & 127) == 0, B200BIT_ERR_ARG, "mpq_chain_build: plan buffer must be 128-byte aligned");
     const int sms = sm_count();
+    static const bool direct_poll = getenv("B200BIT_CHAIN_POLL") ? atoi(getenv("B200BIT_CHAIN_POLL")) != 0 : false;
     // ---- one group size per chain (it fixes the flush interval and the scale-tile geometry of the ring) ----
     int rpg = 0;
     int max_strips = 0;
@@ -117,7 +119,8 @@ int b200bit_mpq_chain_build(const b200bit_chain_node* nodes, int n, int w_bit, i
     const int grid = max_strips < sms ? max_strips : sms;
     const size_t fixed = size_t(IM_XIMG_BYTES) + (2 * IM_WARPS * 32) * sizeof(float) + size_t(n) * sizeof(ChainNode) +
                          (2 * CH_MAX_STAGES + 5) * 8 + 64;
-    int S = CH_MAX_STAGES;
+    static const int slot_cap = getenv("B200BIT_CHAIN_SLOTS") ? atoi(getenv("B200BIT_CHAIN_SLOTS")) : CH_MAX_STAGES;   // sweep hook
+    int S = slot_cap < CH_MAX_STAGES ? (slot_cap < 2 ? 2 : slot_cap) : CH_MAX_STAGES;
     for (; S >= 1; --S)
         if (fixed + size_t(S) * (IM_TILE_BYTES + 2 * sz_bytes) <= size_t(CH_SMEM_LIMIT)) break;
     B200_REQUIRE(S >= 2, B200BIT_ERR_SHAPE, "mpq_chain_build: %d nodes leave no room for the weight ring", n);
@@ -168,9 +171,11 @@ int b200bit_mpq_chain_build(const b200bit_chain_node* nodes, int n, int w_bit, i
                 shadow_at += shadow_bytes(prod.N);
             }
             c.xll = prod.yll;
-            // the counter wait stays as a hint (relaxed, unordered): polling the shadow words only starts once the
-            // producer's strips have been counted, so the retry loop over the data practically never spins
-            prod.off_sig |= 1 << 21;
+            // hint mode: the counter wait stays as a hint (relaxed, unordered) -- polling the shadow words only starts
+            // once the producer's strips have been counted; direct mode: the consumer's warps poll their own rows of the
+            // shadow from the start (one L2 round trip less on the dependent chain, more polling traffic)
+            if (direct_poll) c.wx_node = -1;
+            else prod.off_sig |= 1 << 21;
         } else {
             if (c.wy_node >= 0 && c.wy_node <= c.wx_node) c.wy_node = -1;     // already implied by the wait in front of x
             if (c.wx_node >= 0) cn[c.wx_node].off_sig |= 1 << 20;

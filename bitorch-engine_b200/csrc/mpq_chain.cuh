@@ -36,7 +36,8 @@ constexpr int CH_MAX_STAGES = 7;
 constexpr int CH_SMEM_LIMIT = 227 * 1024;
 constexpr int CH_TRACE_NODES = 32;          // diagnostics: stamps for the first 32 nodes
 constexpr unsigned CH_SPIN_LIMIT = 1u << 22;   // polls before a wait gives up and raises the plan's error flag (~1 s)
-constexpr int CH_THREADS = IM_THREADS + 64;    // sixteen compute warps + the TMA producer warp + the epilogue / dependency warp
+constexpr int CH_THREADS = IM_THREADS + 128;   // sixteen compute warps + one helper warpgroup: the TMA producer warp, the epilogue /
+                                               // dependency warp and two idle warps (register reallocation works on whole warpgroups)
 
 struct __align__(16) ChainNode {     // 64 bytes, device + host
     const uint16_t* x;       // [K] f16 / bf16 bits
@@ -93,10 +94,41 @@ __device__ __forceinline__ void ch_st_ll(uint64_t* p, uint64_t v) {
 __device__ __forceinline__ void ch_hint(unsigned* ctr) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
-__device__ __forceinline__ void ch_spin(const unsigned* ctr, unsigned want, unsigned* err) {
-    unsigned spins = 0;
-    while (ch_ld_acquire(ctr) < want) {
-        if (++spins > CH_SPIN_LIMIT) { atomicExch(err, 1u); break; }
+__device__ __forceinline__ unsigned ch_ld_relaxed(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Wait until *ctr >= want.  A loaded L2 round trip is ~1 us while the weight stream is running, so the polls are
+// PIPELINED: four relaxed loads in flight -- the counter's final value is seen one round trip after it lands instead of
+// 1.5 on average.  `ordered`: the counter orders plain memory (acquire fence at the end); otherwise it
+// is only a hint and the data validates itself.
+__device__ __forceinline__ void ch_spin(const unsigned* ctr, unsigned want, unsigned* err, bool ordered) {
+    unsigned a = ch_ld_relaxed(ctr);
+    if (a < want) {
+        unsigned b = ch_ld_relaxed(ctr);
+        unsigned c = ch_ld_relaxed(ctr);
+        unsigned d = ch_ld_relaxed(ctr);
+        unsigned spins = 0;
+        while (a < want) {          // `a` is the oldest load in flight; three younger ones are behind it
+            a = b; b = c; c = d;
+            d = ch_ld_relaxed(ctr);
+            if (++spins > CH_SPIN_LIMIT) { atomicExch(err, 1u); break; }
+        }
+    }
+    if (ordered) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+// mbarrier wait with a bound: a protocol bug must end in a trap (the launch fails), never in a hung GPU
+__device__ __forceinline__ void ch_mbar_wait(uint32_t bar, unsigned parity) {
+    unsigned tries = 0;
+    while (true) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (++tries > (1u << 22)) asm volatile("trap;");
     }
 }
 
@@ -152,9 +184,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
     unsigned epoch;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(epoch) : "l"(p.counters + n_nodes + 2) : "memory");
 
+    // 20 warps x 96 registers at launch = the CTA's register pool; the helper warpgroup goes down to 56 (frees 5120), the
+    // compute warps up to 104 (take 4096): setmaxnreg.inc blocks until the pool can serve it, so the sums must work out
+    if (warp >= IM_WARPS + 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        return;
+    }
+
     if (warp == IM_WARPS) {
         // ===== TMA producer warp: walks the CTA's tile sequence (node, own strip, k-tile) and keeps the ring full; the
         //       only thing it ever waits for is a free slot, never a layer boundary =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         const unsigned tile_tx = unsigned(IM_TILE_BYTES) + unsigned(p.s_tile_bytes) + unsigned(p.z_tile_bytes);
         const uint32_t leader = um_elect();
         int slot = 0;
@@ -165,7 +205,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
             for (int strip = first_strip(nd); strip < nd.strips; strip += grid) {
                 const int n0 = strip_col(nd, strip);
                 for (int kt = 0; kt < nd.tiles; ++kt) {
-                    im_mbar_wait(smem_u32(&empty[slot]), eph);
+                    ch_mbar_wait(smem_u32(&empty[slot]), eph);
                     const int row = kt * IM_TILE_ROWS;
                     const int g0 = row >> p.rpg_shift;
                     unsigned char* sz = szst + size_t(slot) * 2 * p.sz_bytes;
@@ -184,6 +224,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
         // ===== epilogue / dependency warp: everything of the path that talks to other CTAs.  The compute warps never
         //       wait for each other or for a global-memory round trip: they hand their partial sums over through
         //       red[par] + an mbarrier and go on with the next strip. =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         unsigned use0 = 0u, use1 = 0u;           // how often red[0] / red[1] have been consumed
         int par = 0, waited = -1;
         for (int node = next_node(0); node < n_nodes; node = next_node(node + 1)) {
@@ -193,15 +234,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
                                              // finish in order, so a wait covers every earlier node (siblings skip)
                 waited = nd.wx_node;
                 if (lane == 0) {
-                    ch_spin(p.counters + nd.wx_node, unsigned(nodes_s[nd.wx_node].strips), err_flag);
+                    ch_spin(p.counters + nd.wx_node, unsigned(nodes_s[nd.wx_node].strips), err_flag, nd.xll == nullptr);
                     mbar_arrive(ready);
+                    if constexpr (TRACE) { if (p.trace && node < CH_TRACE_NODES) p.trace[(size_t(bid) * CH_TRACE_NODES + node) * 8 + 4] = st_gtime(); }
                 }
                 __syncwarp();
             }
             for (int strip = first_strip(nd); strip < nd.strips; strip += grid) {
                 const int n0 = strip_col(nd, strip);
                 const unsigned use = par ? use1 : use0;
-                im_mbar_wait(smem_u32(&part[par]), use & 1u);
+                ch_mbar_wait(smem_u32(&part[par]), use & 1u);
                 if constexpr (TRACE) { if (p.trace && lane == 0 && node < CH_TRACE_NODES) p.trace[(size_t(bid) * CH_TRACE_NODES + node) * 8 + 0] = st_gtime(); }
                 const float* rd = red + par * (IM_WARPS * 32);
                 float total = 0.f;
@@ -212,7 +254,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
                 if (par) ++use1; else ++use0;
                 par ^= 1;
                 if (nd.wy_node >= 0) {       // write-after-read / write-after-write: the buffer behind y was used by node wy_node
-                    if (lane == 0) ch_spin(p.counters + nd.wy_node, unsigned(nodes_s[nd.wy_node].strips), err_flag);
+                    if (lane == 0) ch_spin(p.counters + nd.wy_node, unsigned(nodes_s[nd.wy_node].strips), err_flag, true);
                     __syncwarp();
                 }
                 const int width = strip < nd.n28 ? IM_COLS : 24;
@@ -246,6 +288,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
     }
 
     // ===== sixteen compute warps =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int g = lane >> 2, c = lane & 3;
     const int hl = lane >> 4, r16 = lane & 15;
     unsigned char* ximg_w = ximg + warp * IM_WP_BYTES;
@@ -282,15 +325,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
         // ---- read-after-write: the dependency warp has seen the producer's counter ----
         if (nd.wx_node > waited) {
             waited = nd.wx_node;
-            im_mbar_wait(smem_u32(ready), dep_phase);
+            ch_mbar_wait(smem_u32(ready), dep_phase);
             dep_phase ^= 1u;
         }
         // the digit image of x is still in shared memory when the previous node read the very same x (k, v after q; up
         // after gate), this CTA took part in it, and the whole of x fits one staging pass
         const bool keep_image = (nd.off_sig & (1 << 22)) != 0 && prev_node == node - 1 && passes == 1;
         prev_node = node;
-        uint4 xv;
-        auto load_x = [&](int pass) {
+        uint4 xv, xw;             // raw rows of the next two staging passes (a loaded L2 round trip is longer than a pass)
+        auto load_x = [&](int pass, uint4& xv) {
             const int row = (2 * pass + hl) * IM_TILE_ROWS + warp * IM_UNIT_ROWS + r16;
             xv = make_uint4(0u, 0u, 0u, 0u);
             if (nd.xll == nullptr) {
@@ -364,9 +407,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
             if (r16 == 0) wt_w[hl] = __uint_as_float(unsigned(e - 29) << 23);
             __syncwarp();
         };
-        if (!keep_image) load_x(0);
+        if (!keep_image) load_x(0, xv);
+        if (passes > 1) load_x(1, xw);
         CH_TRACE(node, 7);
-        int next_pass = 1 % passes;
+        int next_pass = 2 % passes;
         bool staged_once = keep_image;
 
         for (int strip = first_strip(nd); strip < nd.strips; strip += grid) {
@@ -382,14 +426,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
 #pragma unroll
                 for (int u = 0; u < NT; ++u) {
                     sl[u] = slot + u >= S ? slot + u - S : slot + u;
-                    im_mbar_wait(full_base + sl[u] * 8, slot + u >= S ? (ph ^ 1u) : ph);
+                    ch_mbar_wait(full_base + sl[u] * 8, slot + u >= S ? (ph ^ 1u) : ph);
                     wt[u] = w_base_r + uint32_t(sl[u]) * IM_TILE_BYTES;
                     xt[u] = x_base_r + uint32_t((kt0 + u) & 1) * 512u;
                     sz[u] = sz_base_r + uint32_t(sl[u]) * slot_sz + uint32_t(n0 & 7) * 2u;
                     wunit[u] = __uint_as_float(im_lds32(wp_base_r + 1056u + uint32_t((kt0 + u) & 1) * 4u)) * lane_w;
                     xbu[u] = xb;
                 }
-                if (kt0 == 0) CH_TRACE(node, 4);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const int b = ks >> 1, j = ks & 1;
@@ -469,7 +512,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
                 if ((kt & 1) == 0 && (passes > 1 || !staged_once)) {
                     stage_x();
                     staged_once = true;
-                    if (passes > 1) { load_x(next_pass); next_pass = (next_pass + 1 == passes) ? 0 : next_pass + 1; }
+                    if (passes > 1) { xv = xw; load_x(next_pass, xw); next_pass = (next_pass + 1 == passes) ? 0 : next_pass + 1; }
                     if (kt == 0) CH_TRACE(node, 1);
                 }
                 const bool have0 = kt * IM_TILE_ROWS + unit_row < nd.R;
@@ -502,7 +545,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
             {
                 // red[par] is free again once the epilogue warp has read its previous contents (two strips ago)
                 const unsigned use = rd_par ? use1 : use0;
-                if (use > 0u) im_mbar_wait(smem_u32(&freeb[rd_par]), (use - 1u) & 1u);
+                if (use > 0u) ch_mbar_wait(smem_u32(&freeb[rd_par]), (use - 1u) & 1u);
                 if (rd_par) ++use1; else ++use0;
             }
             float* rd = red + rd_par * (IM_WARPS * 32);

@@ -10,6 +10,14 @@ def _check_cuda(t, name):
         raise RuntimeError(f"{name} must be a CUDA tensor")
 
 
+def _version(t):
+    """torch's in-place version counter, or None for inference tensors (torch.inference_mode(): they do not track one;
+    reading ._version raises there -- the reference works in that mode, e.g. under vLLM-style serving)."""
+    if t.is_inference():
+        return None
+    return t._version
+
+
 def _gidx_is_trivial(g_idx, K, G):
     """True when g_idx == arange(K) // (K // G) (nbit/layer.py:385-386), i.e. groups are contiguous: the fast
     kernels then derive the group from k and never read g_idx.  Checked once per tensor object and version (one
@@ -17,7 +25,7 @@ def _gidx_is_trivial(g_idx, K, G):
     if g_idx is None:
         return True
     tag = getattr(g_idx, "_b200bit_trivial", None)
-    key = (g_idx._version, K, G)
+    key = (_version(g_idx), g_idx.data_ptr(), K, G)
     if tag is not None and tag[0] == key:
         return tag[1]
     if K % G != 0 or g_idx.numel() != K:
@@ -41,13 +49,17 @@ def _input_ready(x, stream):
     the kernels in front.  Writes torch does not version (a foreign kernel writing through data_ptr()) are the usual
     caveat; B200BIT_EARLY=0 switches the overlap off."""
     key = (x.device.index, stream)
+    ver = _version(x)
+    if ver is None:                  # inference tensor: no version counter, so no proof that x is unchanged
+        _prev_x.pop(key, None)
+        return False
     prev = _prev_x.get(key)
-    _prev_x[key] = (x, x._version)
+    _prev_x[key] = (x, ver)
     if prev is None:
         return False
     px, pv = prev
-    return (px.data_ptr() == x.data_ptr() and px.shape == x.shape and px.dtype == x.dtype and px._version == pv
-            and x._version == pv)
+    return (px.data_ptr() == x.data_ptr() and px.shape == x.shape and px.dtype == x.dtype and _version(px) == pv
+            and ver == pv)
 
 
 def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False):
@@ -158,7 +170,10 @@ def mpq_pack_weight(weight, scales, zeros, g_idx, w_bit, asym, zeros_unpacked=Fa
     _check_cuda(weight, "weight")
     K, N = weight.shape
     G = scales.shape[0]
-    weight = weight.to(scales.dtype).contiguous()
+    # an fp32 weight against half parameters keeps its precision: torch promotes the expression to fp32 (utils.py:118-131)
+    if weight.dtype != torch.float32:
+        weight = weight.to(scales.dtype)
+    weight = weight.contiguous()
     zeros = zeros.contiguous()
     if asym and zeros_unpacked:
         zeros = zeros.to(scales.dtype).contiguous()
@@ -169,7 +184,7 @@ def mpq_pack_weight(weight, scales, zeros, g_idx, w_bit, asym, zeros_unpacked=Fa
             weight.data_ptr(), scales.contiguous().data_ptr(), zeros.data_ptr(),
             None if trivial else g_idx.contiguous().data_ptr(), _ptr(None if perm is None else perm.contiguous()),
             out.data_ptr(), K, N, G, w_bit, int(bool(asym)), int(bool(zeros_unpacked)), _cabi.dtype_code(scales.dtype),
-            torch.cuda.current_stream().cuda_stream)
+            _cabi.dtype_code(weight.dtype), torch.cuda.current_stream().cuda_stream)
     _cabi.check(rc)
     return out
 
@@ -203,11 +218,12 @@ def _perm_is_identity(q_perm, K):
     if q_perm is None:
         return True
     tag = getattr(q_perm, "_b200bit_identity", None)
-    if tag is not None and tag[0] == q_perm._version:
+    key = (_version(q_perm), q_perm.data_ptr())
+    if tag is not None and tag[0] == key:
         return tag[1]
     ident = bool(torch.all(q_perm == 0).item()) or bool(
         torch.equal(q_perm.to(torch.int64) & 0xFFFF, torch.arange(K, device=q_perm.device)))
-    q_perm._b200bit_identity = (q_perm._version, ident)
+    q_perm._b200bit_identity = (key, ident)
     return ident
 
 

@@ -38,6 +38,7 @@ class BinaryLinearForward(Function):
         grad_weight = nv_tensor_quant(grad_weight)[0]
         if isinstance(weight, BinaryLinearParameter) and not weight.requires_grad:
             weight.privileged_grad = grad_weight          # stock torch: integer weights cannot receive .grad
+            weight._b200bit_grad_fresh = True
             grad_weight = None
         return unflatten_x(grad_input, lead), grad_weight, None, grad_scale_a, None, None
 

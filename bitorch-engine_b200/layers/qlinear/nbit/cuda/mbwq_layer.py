@@ -44,6 +44,7 @@ class MBWQLinearCudaFunction(Function):
         grad_input = dy.mm(weights.t())
         if wants_wgrad:
             qweight.privileged_grad = x2.t().mm(dy)
+            qweight._b200bit_grad_fresh = True      # DiodeMix.step consumes the mark (stock torch: no .grad on int32)
         del weights
         grad_q = qweight if qweight.requires_grad else None
         return (unflatten_x(grad_input, lead), grad_q) + (None,) * 10

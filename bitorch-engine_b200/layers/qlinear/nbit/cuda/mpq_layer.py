@@ -48,7 +48,8 @@ class MPQLinearCudaFunction(Function):
         grad_input = q_linear_cuda.mpq_grad_input(qweight.data, qweight.scales, qweight.zeros, qweight.g_idx, dy,
                                                   ctx.a_bit, qweight.w_bit, qweight.asym)
         if wants_wgrad:
-            qweight.privileged_grad = x2.t().mm(dy)                      # [K,M] @ [M,N], cuBLAS (mpq_layer.py:116)
+            qweight.privileged_grad = x2.t().mm(dy)
+            qweight._b200bit_grad_fresh = True      # DiodeMix.step consumes the mark (stock torch: no .grad on int32)                      # [K,M] @ [M,N], cuBLAS (mpq_layer.py:116)
         grad_q = qweight if qweight.requires_grad else None              # the reference returns the parameter itself
         return unflatten_x(grad_input, lead), grad_q, None, None, None, None, None, None, None, None
 

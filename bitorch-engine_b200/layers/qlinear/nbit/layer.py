@@ -69,13 +69,11 @@ class MPQLinearBase(nn.Module):
                                           requires_grad=self.requires_grad, w_bit=b, asym=self.asym,
                                           group_size=self.group_size)
         # weight-gradient slot handed to the autograd Function (nbit/layer.py:382).  The reference allocates a dense
-        # [K,N] tensor per layer; a stride-0 view keeps the shape without the memory.  When integer tensors cannot
-        # require grad it doubles as the autograd hook that makes backward() run.
-        if self.requires_grad:
-            carrier = torch.zeros((1,), dtype=self.dtype, requires_grad=not TORCH_INT_GRADIENTS)
-            self.privileged_grad = carrier.expand(K, N)
-        else:
-            self.privileged_grad = None
+        # [K,N] tensor per layer; here only a one-element LEAF is stored (deepcopy / peft / EMA copy the module like any
+        # other) and the `privileged_grad` property hands out a stride-0 [K,N] view of it.  When integer tensors cannot
+        # require grad the leaf doubles as the autograd hook that makes backward() run.
+        self._grad_carrier = (torch.zeros((1,), dtype=self.dtype, requires_grad=not TORCH_INT_GRADIENTS)
+                              if self.requires_grad else None)
         self.register_buffer("g_idx", (torch.arange(K, dtype=torch.int32) // self.group_size).contiguous())
         self.register_buffer("bias", torch.zeros((N,), dtype=self.dtype))
         self.register_buffer("wf", torch.arange(0, 32, b, dtype=torch.int32).unsqueeze(0))
@@ -83,6 +81,23 @@ class MPQLinearBase(nn.Module):
             self.init_gba()
         else:
             self.init_gptq()
+
+    @property
+    def privileged_grad(self):
+        """[K, N] view of the gradient carrier (None for frozen layers); built on access, never stored."""
+        c = self.__dict__.get("_grad_carrier")
+        if c is None:
+            return None
+        return c.expand(self.in_channels, self.out_channels)
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .half(): move the carrier with the module (it is neither a Parameter nor a buffer)
+        out = super()._apply(fn, *args, **kwargs)
+        c = self.__dict__.get("_grad_carrier")
+        if c is not None:
+            moved = fn(c.detach())
+            self._grad_carrier = moved.clone().requires_grad_(c.requires_grad) if moved.is_floating_point() else c
+        return out
 
     def _groups(self) -> int:
         return math.ceil(self.in_channels / self.group_size)

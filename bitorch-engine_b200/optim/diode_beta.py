@@ -38,12 +38,23 @@ class DiodeMix(Optimizer):
             beta1, beta2 = group["betas"]
             for p in group["params"]:
                 is_mpq = isinstance(p, MPQWeightParameter)
-                grad = p.privileged_grad if is_mpq else p.grad
-                # the reference skips on `p.grad is None` (diode_beta.py:118-119); with stock torch an integer weight
-                # never receives .grad, so the privileged gradient decides for MPQ parameters
-                if grad is None or (is_mpq and grad.shape != (p.shape[0] * 32 // max(p.w_bit, 1), p.shape[1])
-                                    and "rank" not in group):
+                is_bin = isinstance(p, BinaryLinearParameter)
+                # The reference skips a parameter whose .grad is None (diode_beta.py:118-119).  On stock torch an integer
+                # weight never receives .grad: backward() then leaves the weight gradient in p.privileged_grad and marks
+                # it fresh, and step() consumes the mark -- a layer that did not run backward in this iteration is
+                # skipped exactly as in the reference (neither the forward pass's placeholder nor a gradient of an
+                # earlier iteration is ever applied).
+                if is_mpq:
+                    fresh = getattr(p, "_b200bit_grad_fresh", False) or p.grad is not None
+                    grad = p.privileged_grad if fresh else None
+                elif is_bin and p.grad is None:
+                    grad = getattr(p, "privileged_grad", None) if getattr(p, "_b200bit_grad_fresh", False) else None
+                else:
+                    grad = p.grad
+                if grad is None:
                     continue
+                if is_mpq or is_bin:
+                    p._b200bit_grad_fresh = False
                 if grad.is_sparse:
                     raise RuntimeError("Adam does not support sparse gradients, please consider SparseAdam instead")
                 state = self.state[p]
@@ -64,7 +75,7 @@ class DiodeMix(Optimizer):
                     else:
                         state["exp_avg_l"] = torch.zeros_like(grad, dtype=self.dtype)
                         state["exp_avg_s"] = torch.zeros_like(grad, dtype=self.dtype)
-                if is_mpq or isinstance(p, BinaryLinearParameter):
+                if is_mpq or is_bin:
                     type(p).update(qweight=p, exp_avg_s=state["exp_avg_s"], exp_avg_l=state["exp_avg_l"],
                                    step=state["step"], lr=group["lr"], weight_decay=group["weight_decay"], beta1=beta1,
                                    beta2=beta2, correct_bias=group["correct_bias"], eps=group["eps"], dtype=self.dtype,
@@ -86,3 +97,12 @@ class DiodeMix(Optimizer):
                 if group["weight_decay"] > 0.0:
                     p.add_(p, alpha=(-group["lr"] * group["weight_decay"]))
         return loss
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """Also drops the privileged gradients of quantised parameters (stock torch keeps them outside .grad)."""
+        super().zero_grad(set_to_none=set_to_none)
+        for group in self.param_groups:
+            for p in group["params"]:
+                if getattr(p, "_b200bit_grad_fresh", False):
+                    p._b200bit_grad_fresh = False
+                    p.privileged_grad = None

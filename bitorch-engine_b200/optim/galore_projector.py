@@ -30,13 +30,23 @@ class GaLoreProjector:
         return torch.matmul(self.ortho_matrix[0].t(), full_rank_grad) @ self.ortho_matrix[1].t()
 
     def project_back(self, low_rank_grad):
-        m = self.ortho_matrix
-        if isinstance(m, list):
-            out = torch.matmul(m[0], low_rank_grad) @ m[1]
-        elif low_rank_grad.shape[-1] == m.shape[0]:          # projected on the right
+        """galore_projector.py:85-107: the side follows proj_type (and, for std / reverse_std, the shape of the LOW-rank
+        gradient) -- not the shapes of the stored factor, which are ambiguous for square weights."""
+        m, t = self.ortho_matrix, self.proj_type
+        tall = low_rank_grad.shape[0] >= low_rank_grad.shape[1]
+        if t == "std":
+            out = torch.matmul(low_rank_grad, m) if tall else torch.matmul(m, low_rank_grad)
+        elif t == "reverse_std":
+            wide = low_rank_grad.shape[0] <= low_rank_grad.shape[1]
+            out = torch.matmul(m, low_rank_grad) if wide else torch.matmul(low_rank_grad, m)
+        elif t == "right":
             out = torch.matmul(low_rank_grad, m)
-        else:
+        elif t == "left":
             out = torch.matmul(m, low_rank_grad)
+        elif t == "full":
+            out = torch.matmul(m[0], low_rank_grad) @ m[1]
+        else:
+            raise ValueError(f"unknown proj_type {t}")
         return out * self.scale
 
     def get_orthogonal_matrix(self, weights, rank, type):

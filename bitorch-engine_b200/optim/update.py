@@ -17,14 +17,16 @@ def _bias_corrected_step(lr, beta1, beta2, step, correct_bias):
 
 
 def _mpq_step_torch(qweight, exp_avg_s, exp_avg_l, step, step_size, beta1, beta2, eps, dtype, projector, grad):
-    """Unfused path for the cases the kernel does not cover (act-order g_idx, GaLore projector, MBWQ q_perm):
-    the same arithmetic spelled with torch ops on top of the dequant / pack kernels."""
-    from ..layers.qlinear.nbit.cuda.utils import unpack_qweight, pack_fp_weight
-    from ..extensions import q_linear_cuda
-    w = unpack_qweight(qweight).to(dtype)
-    z_unpacked = None
-    if qweight.asym:
-        z_unpacked = q_linear_cuda.unpack_zeros(qweight.zeros, qweight.w_bit).to(dtype)
+    """Unfused path for what the kernel does not cover (act-order g_idx, GaLore projector, MBWQ q_perm): the reference's
+    own sequence (model_helper.py:485-523) on top of the dequant / pack kernels -- gptq_style_unpacking, Adam moments,
+    projection back, update_zeros every 5th step, pack_fp_weight."""
+    from ..layers.qlinear.nbit.cuda.utils import pack_fp_weight
+    from ..utils.quant_operators import gptq_style_unpacking
+    from ..utils.model_helper import update_zeros
+    w, z_unpacked = gptq_style_unpacking(qweight)
+    w = w.to(dtype)
+    if z_unpacked is not None:
+        z_unpacked = z_unpacked.to(dtype)
     exp_avg_l.mul_(beta1).add_(grad, alpha=(1.0 - beta1))
     exp_avg_s.mul_(beta2).addcmul_(grad, grad, value=1.0 - beta2)
     denom = exp_avg_s.sqrt().add_(eps)
@@ -33,24 +35,15 @@ def _mpq_step_torch(qweight, exp_avg_s, exp_avg_l, step, step_size, beta1, beta2
         norm_grad = projector.project_back(norm_grad.to(dtype))
     w.add_(norm_grad, alpha=-step_size)
     if int(step.item()) % 5 == 0:
-        K = w.shape[0]
-        G = qweight.scales.shape[0]
-        if qweight.layer_type == 2:
-            perm = qweight.q_perm.long()
-            zg = norm_grad.index_select(0, perm).view(G, K // G, -1).mean(1)
+        if qweight.layer_type == 1 and not qweight.asym:
+            # symmetric MPQ: the reference cannot reach this point (its unpack raises); the MBWQ rule without the gather
+            order = torch.argsort(qweight.g_idx.long(), dim=0)
+            G = qweight.scales.shape[0]
+            zg = norm_grad[order].view(G, w.shape[0] // G, -1).mean(1)
             qweight.zeros.add_((step_size * zg).to(qweight.zeros.dtype))
-        elif qweight.asym:
-            gi = qweight.g_idx.long()
-            zu = z_unpacked[gi] + step_size * norm_grad
-            order = torch.argsort(gi, dim=0)
-            zmean = zu[order].view(G, K // G, -1).mean(1)
-            qweight.zeros = q_linear_cuda.pack_zeros(zmean, qweight.w_bit)
         else:
-            gi = qweight.g_idx.long()
-            order = torch.argsort(gi, dim=0)
-            zg = norm_grad[order].view(G, K // G, -1).mean(1)
-            qweight.zeros.add_((step_size * zg).to(qweight.zeros.dtype))
-    qweight.data = pack_fp_weight(w.to(qweight.scales.dtype) if not qweight.asym else w, qweight, z_unpacked)
+            update_zeros(qweight, w, norm_grad, step_size, z_unpacked)
+    qweight.data = pack_fp_weight(w, qweight, z_unpacked if qweight.asym else None)
 
 
 def qweight_update_fn(qweight, exp_avg_s=None, exp_avg_l=None, step=None, lr=1e-4, weight_decay=0.0, beta1=0.99,

@@ -83,3 +83,27 @@ def load_checkpoint(model: torch.nn.Module, checkpoint_path: str, qweight_only: 
     pack_bie_layers(model, qweight_only)
     checkpoint = torch.load(checkpoint_path)
     model.load_state_dict(checkpoint["state_dict"], strict=False)
+
+
+def update_zeros(qweight, w, norm_grad, step_size, z_unpacked=None):
+    """The every-5th-step zero-point update of DiodeMix (model_helper.py:330-360).
+
+    MBWQ (layer_type 2): zeros += step_size * mean over each group of the q_perm-gathered normalised gradient.
+    MPQ  (layer_type 1, g_idx given): the integer zero points follow their rows' gradients,
+         zeros = pack(mean_g(z_unpacked[g_idx] + step_size * norm_grad)), stored packed (the buffer object is replaced)."""
+    from .quant_operators import gptq_style_zeros_packing
+    groups, cols = qweight.scales.size(0), qweight.scales.size(-1)
+    if qweight.layer_type == 2:
+        index = qweight.q_perm.unsqueeze(1).repeat(1, w.size(1)).long()
+        zeros_grad = torch.gather(norm_grad, dim=0, index=index)
+        qweight.zeros.add_(step_size * zeros_grad.view(-1, w.size(0) // groups, cols).mean(1))
+    elif qweight.layer_type == 1 and qweight.g_idx is not None:
+        g_idx = qweight.g_idx.long()
+        zeros_unpack = z_unpacked[g_idx]
+        zeros_unpack.add_(step_size * norm_grad)
+        order = torch.argsort(g_idx, dim=0)
+        zeros = zeros_unpack[order, :].view(-1, w.size(0) // groups, cols).mean(1)
+        qweight.zeros = gptq_style_zeros_packing(zeros, qweight.w_bit, zeros.size(-1), qweight.group_size)
+    else:
+        raise NotImplementedError(
+            "qweight.layer_type: '{}' has not been supported yet.".format(str(qweight.layer_type)))

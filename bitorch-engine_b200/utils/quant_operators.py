@@ -110,3 +110,51 @@ def gptq_style_zeros_packing(zeros: torch.Tensor, w_bit: int, out_features: int,
     z = (zeros.reshape(zeros.shape[0], out_features // 32 * w_bit, per).to(torch.int32) - 1) & ((1 << w_bit) - 1)
     shifts = torch.arange(0, 32, w_bit, device=zeros.device, dtype=torch.int32)
     return torch.bitwise_left_shift(z, shifts.view(1, 1, -1)).sum(dim=-1).to(torch.int32)
+
+
+def gptq_style_unpacking(qweight):
+    """(weights [K,N], zeros) of an MPQWeightParameter, the optimizer-side unpack (quant_operators.py:310-345).
+
+      asym (packed qzeros)      : weights = scales[g] * (q - zq[g]),  zeros = integer zero points [G,N] (field + 1)
+      sym, g_idx None (MBWQ)    : weights = q * scales - zeros, rows scattered through q_perm,
+                                  zeros = the fp zeros repeated per row [K,N]
+      sym with g_idx            : weights = q * scales[g] - zeros[g]; the reference returns an unbound name here
+                                  (UnboundLocalError), this returns zeros = None
+    CUDA tensors run the one-pass dequant kernel (bit-identical roundings, tests/test_gpu_mpq_aux.py); CPU tensors are
+    unpacked with the reference's own torch arithmetic (host helper)."""
+    w_bit, asym = qweight.w_bit, bool(qweight.asym)
+    data = qweight.data
+    g_idx = getattr(qweight, "g_idx", None)
+    if asym:
+        shifts = torch.arange(0, 32, w_bit, dtype=torch.int32, device=data.device)
+        zq = torch.bitwise_right_shift(qweight.zeros.unsqueeze(2), shifts.view(1, 1, -1)) & ((1 << w_bit) - 1)
+        zeros = (zq + 1).to(torch.int16 if w_bit == 8 else torch.int8).reshape(-1, data.size(-1))
+    elif g_idx is None:
+        rep = (data.size(0) * 32 // w_bit) // qweight.zeros.size(0)
+        zeros = qweight.zeros.unsqueeze(1).repeat(1, rep, 1).view(-1, qweight.zeros.size(-1))
+    else:
+        zeros = None
+    if data.is_cuda:
+        from ..extensions import q_linear_cuda
+        perm = None
+        if not asym and g_idx is None:
+            K = data.size(0) * 32 // w_bit
+            perm = None if q_linear_cuda._perm_is_identity(qweight.q_perm, K) else qweight.q_perm
+        weights = q_linear_cuda.mpq_dequant(data, qweight.scales, qweight.zeros, g_idx, w_bit, asym, perm=perm)
+        return weights, zeros
+    shifts = torch.arange(0, 32, w_bit, dtype=torch.int32)
+    q = (torch.bitwise_right_shift(data.unsqueeze(1), shifts.view(1, -1, 1)) & ((1 << w_bit) - 1))
+    q = q.to(torch.int16 if w_bit == 8 else torch.int8).view(-1, data.size(-1))
+    if asym:
+        gi = g_idx.long()
+        weights = qweight.scales[gi] * (q - zeros[gi])
+    elif g_idx is None:
+        rep = q.size(0) // qweight.scales.size(0)
+        scales = qweight.scales.unsqueeze(1).repeat(1, rep, 1).view(-1, qweight.scales.size(-1))
+        weights = q.mul(scales) - zeros
+        index = qweight.q_perm.unsqueeze(1).repeat(1, weights.size(1)).long()
+        weights.scatter_(dim=0, index=index, src=weights.clone())
+    else:
+        gi = g_idx.long()
+        weights = q * qweight.scales[gi] - qweight.zeros[gi]
+    return weights, zeros

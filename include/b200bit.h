@@ -152,10 +152,12 @@ B200BIT_API int b200bit_exl2_dequant(const int32_t* qweight, const void* scales,
  * pack_fp_weight (utils.py:72-147): sym clamp(rint(rnd(rnd(w+z)/s))), asym clamp(rint(rnd(rnd(w/s)+zq))).
  * zeros: sym dtype [G,N]; asym packed int32 [G,N*w_bit/32] (zeros_unpacked=0) or integer zero points stored as dtype
  * [G,N] (zeros_unpacked=1: the `unpacked_zeros` argument).  perm: optional int16 [K] row gather (MBWQ q_perm).
+ * weight_dtype: dtype of `weight` -- `dtype` (that of scales / zeros) or F32: the optimizer packs its fp32 master weight
+ * against half parameters, torch then promotes and evaluates (and rounds) the whole expression in fp32.
  * ------------------------------------------------------------------------------------------------------------ */
 B200BIT_API int b200bit_mpq_pack_weight(const void* weight, const void* scales, const void* zeros, const int32_t* g_idx,
                                         const int16_t* perm, int32_t* qweight_out, int K, int N, int G, int w_bit,
-                                        int asym, int zeros_unpacked, int dtype, void* stream);
+                                        int asym, int zeros_unpacked, int dtype, int weight_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused DiodeMix update of an MPQ weight (one kernel): unpack -> Adam moments -> normalised gradient -> step ->
@@ -196,6 +198,16 @@ B200BIT_API int b200bit_binary_relayout(const uint8_t* in, uint8_t* out, int N, 
                                         int canon_stride_bytes, void* stream);
 B200BIT_API int b200bit_binary_gemm(const uint8_t* x_bits, const uint8_t* w_bits, void* out, int M, int N, int K,
                                     int stride_bytes, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HOST (CPU) binary Linear -- the reference's `binary_linear_cpp` extension for BinaryLinearCPP
+ * (binary/cpp/binary_linear.cpp:494-518: forward(input, weights, m, n, k), w_pack(weights, n, k)).  All pointers are
+ * HOST pointers; fp32 input only, as the reference (data_ptr<float>, :425).  Same arithmetic as the CUDA path; packed
+ * weight layout of the CPU extension: byte (k/8)*N + n, bit j (LSB first) = sign(w[n, 8*(k/8)+j]) (:80-145).
+ * ------------------------------------------------------------------------------------------------------------ */
+B200BIT_API int b200bit_cpu_binary_pack(const float* weights_host, uint8_t* out_host, int n, int k);
+B200BIT_API int b200bit_cpu_binary_forward(const float* x_host, const void* weights_host, int weights_packed,
+                                           float* out_host, int m, int n, int k, int threads);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Wire-format conversions of the reference's `functions_cuda` extension (bitorch_engine/functions/cuda/

@@ -252,6 +252,115 @@ def gen_helpers():
     print("helper_cases.npz:", {k: v.shape for k, v in out.items()})
 
 
+def gen_optim2():
+    """The unfused branches of the reference's MPQ weight update + its optimizer-side helpers, run on CPU:
+      * gptq_style_unpacking (utils/quant_operators.py:310-345): asym act-order, asym contiguous, MBWQ (q_perm scatter)
+      * update_zeros (utils/model_helper.py:330-360): both branches
+      * qweight_update_fn (model_helper.py:485-523) with act-order g_idx, with an MBWQ (layer_type 2) weight, and with a
+        GaLoreProjector (one SVD: update_proj_gap larger than the run, so CPU / GPU singular-vector signs cancel)
+      * GaLoreProjector.project / project_back for every proj_type on tall, wide and square gradients."""
+    from bitorch_engine.layers.qlinear.nbit import MPQWeightParameter
+    from bitorch_engine.utils.model_helper import qweight_update_fn, update_zeros
+    from bitorch_engine.utils.quant_operators import gptq_style_unpacking
+    from bitorch_engine.optim.galore_projector import GaLoreProjector
+
+    out = {}
+    K, N = 256, 64
+
+    def mpq(w_bit, group, act, seed):
+        qweight, scales, zeros, g_idx, _, _ = make_inputs(K, N, w_bit, group, "f16", True, act, seed)
+        return MPQWeightParameter(qweight.clone(), requires_grad=False, scales=scales, zeros=zeros.clone(), g_idx=g_idx,
+                                  w_bit=w_bit, asym=True, group_size=group, layer_type=1)
+
+    def mbwq(w_bit, group, seed):
+        qweight, scales, zeros, _, _, _ = make_inputs(K, N, w_bit, group, "f16", False, False, seed)
+        gen = torch.Generator().manual_seed(seed + 77)
+        q_perm = torch.randperm(K, generator=gen).to(torch.short)
+        return MPQWeightParameter(qweight.clone(), requires_grad=False, scales=scales, zeros=zeros.clone(), g_idx=None,
+                                  w_bit=w_bit, asym=False, group_size=group, layer_type=2, q_perm=q_perm)
+
+    def dump_param(name, qp):
+        out[f"{name}_qweight0"] = qp.data.numpy().copy()
+        out[f"{name}_scales"] = _bits(qp.scales)
+        out[f"{name}_zeros0"] = qp.zeros.numpy().copy() if qp.zeros.dtype == torch.int32 else _bits(qp.zeros)
+        if qp.g_idx is not None:
+            out[f"{name}_g_idx"] = qp.g_idx.numpy().copy()
+        if getattr(qp, "q_perm", None) is not None:
+            out[f"{name}_q_perm"] = qp.q_perm.numpy().copy()
+
+    # ---- gptq_style_unpacking ----
+    unpack_cases = []
+    for name, qp, meta in (("u0", mpq(4, 64, True, 8100), "mpq,4,64,1"), ("u1", mpq(2, 32, False, 8101), "mpq,2,32,0"),
+                           ("u2", mpq(8, 128, True, 8102), "mpq,8,128,1"), ("u3", mbwq(4, 64, 8103), "mbwq,4,64,0"),
+                           ("u4", mbwq(2, 32, 8104), "mbwq,2,32,0")):
+        dump_param(name, qp)
+        w, z = gptq_style_unpacking(qp)
+        out[f"{name}_w"] = _bits(w)
+        out[f"{name}_z"] = z.numpy().copy() if z.dtype in (torch.int8, torch.int16) else _bits(z)
+        unpack_cases.append(f"{name},{meta}")
+    out["unpack_cases"] = np.array(unpack_cases)
+
+    # ---- update_zeros ----
+    gen = torch.Generator().manual_seed(8200)
+    for name, qp in (("z0", mpq(4, 64, True, 8201)), ("z1", mbwq(4, 64, 8202))):
+        dump_param(name, qp)
+        w, z = gptq_style_unpacking(qp)
+        w, z = w.float(), z.float()
+        ng = torch.randn((K, N), generator=gen)
+        out[f"{name}_norm_grad"] = ng.numpy().copy()
+        update_zeros(qp, w, ng, 0.37, z)
+        out[f"{name}_zeros1"] = qp.zeros.numpy().copy() if qp.zeros.dtype == torch.int32 else _bits(qp.zeros)
+
+    # ---- qweight_update_fn, unfused branches ----
+    upd_cases = []
+    def run_update(name, qp, odt, projector, iters=6):
+        tdt = TORCH_DT[odt]
+        gen = torch.Generator().manual_seed(8300 + len(upd_cases))
+        dump_param(name, qp)
+        step = torch.zeros(1)
+        m = v = None
+        for it in range(1, iters + 1):
+            grad = (torch.randn((K, N), generator=gen) * 0.05).half()
+            out[f"{name}_grad{it}"] = _bits(grad)
+            g = grad
+            if projector is not None:
+                g = projector.project(grad.to(tdt), step.item())
+            if m is None:
+                m = torch.zeros_like(g, dtype=tdt)
+                v = torch.zeros_like(g, dtype=tdt)
+            qweight_update_fn(qweight=qp, exp_avg_s=v, exp_avg_l=m, step=step, lr=2e-3, weight_decay=0.0, beta1=0.99,
+                              beta2=0.9999, eps=1e-6, dtype=tdt, correct_bias=True, projector=projector, grad=g)
+            out[f"{name}_qweight{it}"] = qp.data.numpy().copy()
+            out[f"{name}_zeros{it}"] = qp.zeros.numpy().copy() if qp.zeros.dtype == torch.int32 else _bits(qp.zeros)
+    run_update("f0", mpq(4, 64, True, 8301), "f32", None); upd_cases.append("f0,mpq_act,4,64,f32,0")
+    run_update("f1", mbwq(4, 64, 8302), "f32", None); upd_cases.append("f1,mbwq,4,64,f32,0")
+    run_update("f2", mbwq(2, 32, 8303), "f16", None); upd_cases.append("f2,mbwq,2,32,f16,0")
+    run_update("f3", mpq(4, 128, False, 8304), "f32", GaLoreProjector(16, update_proj_gap=1000, scale=0.5, proj_type="std"))
+    upd_cases.append("f3,mpq_galore,4,128,f32,16")
+    out["update_cases"] = np.array(upd_cases)
+
+    # ---- GaLoreProjector ----
+    gal = []
+    gid = 0
+    for shape in ((96, 48), (48, 96), (64, 64)):
+        for pt in ("std", "reverse_std", "right", "left", "full"):
+            gen = torch.Generator().manual_seed(8400 + gid)
+            pr = GaLoreProjector(8, update_proj_gap=2, scale=0.25, proj_type=pt)
+            name = f"g{gid}"
+            for it in range(3):
+                gfull = torch.randn(shape, generator=gen)
+                low = pr.project(gfull, it)
+                back = pr.project_back(low)
+                out[f"{name}_full{it}"] = gfull.numpy().copy()
+                out[f"{name}_low{it}"] = low.numpy().copy()
+                out[f"{name}_back{it}"] = back.numpy().copy()
+            gal.append(f"{name},{shape[0]},{shape[1]},{pt}")
+            gid += 1
+    out["galore_cases"] = np.array(gal)
+    np.savez_compressed(os.path.join(GOLD, "optim2_cases.npz"), **out)
+    print(f"optim2: {len(unpack_cases)} unpack, {len(upd_cases)} update, {len(gal)} galore cases -> tests/golden/optim2_cases.npz")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["nbit"]
     for w in what:

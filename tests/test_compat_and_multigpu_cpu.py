@@ -27,6 +27,11 @@ def test_reference_module_paths_resolve():
             "'q4_unpack','q4_unpack_and_scaling']);"
             "from bitorch_engine.functions.cuda import q4_pack_tensor, q4_unpack_tensor, q4_unpack_and_scaling_tensor;"
             "from bitorch_engine.functions.cuda.functions import tensor_to_packed_uint8, unpack_uint8_tensor;"
+            "c = importlib.import_module('bitorch_engine.extensions.binary_linear_cpp');"
+            "assert all(hasattr(c, n) for n in ['forward','w_pack']);"
+            "from bitorch_engine.layers.qlinear.binary.cpp import BinaryLinearCPP;"
+            "from bitorch_engine.utils.quant_operators import gptq_style_unpacking, gptq_style_zeros_packing;"
+            "from bitorch_engine.utils.model_helper import update_zeros, qweight_update_fn;"
             "print('ok')")
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "compat"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")

@@ -61,4 +61,4 @@ for i in range(n):
     K, N = chain.nodes[i][5], chain.nodes[i][6]
     extra = f" | period {row[3][2] - prev_written}" if prev_written is not None else ""
     prev_written = row[3][2]
-    print(f"node {i:3d} {names[i % 7]:>4} {K}x{N}: enter {row[6]} xhere {row[7]} staged {row[1]} landed {row[4]} pair0 {row[5]} loopend(w0) {row[2]} partials {row[0]} written {row[3]}{extra}")
+    print(f"node {i:3d} {names[i % 7]:>4} {K}x{N}: enter {row[6]} xhere {row[7]} staged {row[1]} deppoll {row[4]} pair0 {row[5]} loopend(w0) {row[2]} partials {row[0]} written {row[3]}{extra}")
