@@ -62,6 +62,9 @@ def _input_ready(x, stream):
             and ver == pv)
 
 
+MPQ_FUSED_MAX_ROWS = 32
+
+
 def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False):
     """y[M,N] = x[M,K] @ dequant(qweight)  (q_linear_cuda.cpp:258-270 -> mpq_linear_cuda_kernel.cu:603-626).
 
@@ -91,6 +94,11 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         if not _gidx_is_trivial(g_idx, K, G):
             raise NotImplementedError("DecodeChain: act-order g_idx is not supported inside a chain")
         return rec.add(x, qweight, scales, zeros, w_bit, asym)
+    if M > MPQ_FUSED_MAX_ROWS and x.dtype != torch.float32:
+        # large batches (prefill, training): dequantise ONCE (one kernel, bit-identical to unpack_qweight) + dense GEMM --
+        # the switch the reference makes at the same point (mpq_layer.py:59-63); one pass over the packed matrix instead of
+        # re-streaming it per 32-row group
+        return torch.matmul(x, mpq_dequant(qweight, scales, zeros, g_idx, w_bit, asym))
     x = x.contiguous()
     qweight = qweight.contiguous()
     scales = scales.contiguous()
@@ -293,9 +301,38 @@ def mbwq_exl2fp_weight(qweight, scales, zeros, q_perm, q_group_map, rows):
     return out
 
 
+# above this many rows the dequantise-once + dense GEMM pair wins over re-streaming the packed matrix per 8-row group
+# (the reference switches to its reconstruct + cuBLAS path at 50 rows, mbwq_linear_cuda_kernel.cu:947-957)
+EXL2_FUSED_MAX_ROWS = 32
+
+
 def mbwq_exl2_forward(x, qweight, scales, zeros, q_perm, q_group_map, rows, use_cublas=False):
-    """y = x @ W_exl2 (q_linear_cuda.cpp:338-354 -> :926-1007).  Round 1: dequantise (one kernel) + cuBLAS for every M --
-    the path the reference itself takes above 32 rows (:947-957); a fused mixed-bit GEMV is listed in DESIGN.md "next"."""
+    """y = x[:, q_perm] @ W_exl2 (q_linear_cuda.cpp:338-354 -> :926-1007).  Up to 32 rows: ONE fused mixed-bit kernel
+    (csrc/exl2_gemv.cu: the packed matrix is read once, no fp16 copy of W, no cuBLAS); more rows, or use_cublas=True:
+    dequantise (one kernel) + dense matmul, the path the reference itself takes for large batches."""
     _check_cuda(x, "x")
-    W = mbwq_exl2fp_weight(qweight, scales, zeros, q_perm, q_group_map, rows)
-    return torch.matmul(x, W)
+    _check_cuda(qweight, "qweight")
+    if x.dtype != torch.float16:
+        raise TypeError("mbwq_exl2_forward: x must be torch.half")
+    if x.dim() != 2:
+        raise ValueError("mbwq_exl2_forward expects a 2-D input (use flatten_x)")
+    M, K = x.shape
+    N = qweight.shape[1]
+    if q_group_map.numel() != 2 * K:
+        raise ValueError(f"q_group_map has {q_group_map.numel()} entries, expected 2*K = {2 * K}")
+    if use_cublas or M > EXL2_FUSED_MAX_ROWS:
+        W = mbwq_exl2fp_weight(qweight, scales, zeros, q_perm, q_group_map, rows)
+        return torch.matmul(x, W)
+    import ctypes
+    y = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    if M == 0:
+        return y
+    rows6 = (ctypes.c_int * 6)(*[int(r) for r in rows[:6]])
+    perm = None if (q_perm is None or _perm_is_identity(q_perm, K)) else q_perm.contiguous()
+    with torch.cuda.device(x.device):
+        rc = _cabi.lib().b200bit_exl2_forward(x.contiguous().data_ptr(), qweight.contiguous().data_ptr(),
+                                              scales.contiguous().data_ptr(), zeros.contiguous().data_ptr(), _ptr(perm),
+                                              q_group_map.contiguous().data_ptr(), y.data_ptr(), M, K, N, rows6,
+                                              torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc)
+    return y

@@ -109,6 +109,28 @@ def test_exl2_dequant_and_forward(K, N, si, permute):
         assert rel_fro(to_np_f32(y), to_np_f32(x).astype(np.float64) @ Wo.astype(np.float64)) <= 2e-3
 
 
+@pytest.mark.parametrize("K,N", [(4096, 4096), (4096, 11008), (11008, 4096)])
+@pytest.mark.parametrize("M", [1, 5, 8, 32])
+def test_exl2_fused_forward_llama_shapes(K, N, M):
+    """BASELINE config #3 "(ii) MBWQ exl2 within-layer bits=[4,2], bits_prop=[0.75,0.25], group 32" at the Llama-7B
+    shapes: the fused mixed-bit kernel (no cuBLAS, W never materialised) against x @ exl2fp(W), where exl2fp is pinned
+    bit-exactly to the oracle / the reference extension above.  fp32 accumulation of the exact model vs the fp16-rounded
+    W: 2e-3 normwise (the reference's own bound is |diff| < 2, test_nbit_linear_mixbits.py:108)."""
+    from bitorch_engine_b200.extensions import q_linear_cuda
+    layer = _make_exl2(K, N, STRATEGIES[0], seed=K + N, permute=True)
+    x = torch.randn((M, K), device="cuda").half()
+    y = q_linear_cuda.mbwq_exl2_forward(x, layer.qweight.data, layer.scales, layer.zeros, layer.q_perm, layer.q_group_map,
+                                        layer.rows)
+    W = q_linear_cuda.mbwq_exl2fp_weight(layer.qweight.data, layer.scales, layer.zeros, layer.q_perm, layer.q_group_map,
+                                         layer.rows)
+    ref = (x.double() @ W.double()).cpu().numpy()
+    assert y.dtype == torch.float16 and tuple(y.shape) == (M, N)
+    assert rel_fro(to_np_f32(y), ref) <= 2e-3
+    yc = q_linear_cuda.mbwq_exl2_forward(x, layer.qweight.data, layer.scales, layer.zeros, layer.q_perm, layer.q_group_map,
+                                         layer.rows, use_cublas=True)
+    assert rel_fro(to_np_f32(yc), ref) <= 2e-3
+
+
 def test_against_reference_cuda_extension_when_available():
     ref = _ref_ext("q_linear_cuda")
     if ref is None:
@@ -139,3 +161,11 @@ def test_against_reference_cuda_extension_when_available():
     a = ref.mbwq_exl2fp_weight(layer.qweight.data, layer.scales, layer.zeros, layer.q_perm, layer.q_group_map, layer.rows[:7])
     b = q_linear_cuda.mbwq_exl2fp_weight(layer.qweight.data, layer.scales, layer.zeros, layer.q_perm, layer.q_group_map, layer.rows)
     assert torch.equal(a, b)
+    # exl2 fused forward vs the reference's mixed-bit GEMV (fp16 accumulation + atomics on their side: 3e-2 normwise)
+    for M in (1, 4):
+        x = torch.randn((M, 1024), device="cuda").half()
+        ya = ref.mbwq_exl2_forward(x, layer.qweight.data, layer.scales, layer.zeros, layer.q_perm, layer.q_group_map,
+                                   layer.rows[:7], False)
+        yb = q_linear_cuda.mbwq_exl2_forward(x, layer.qweight.data, layer.scales, layer.zeros, layer.q_perm, layer.q_group_map,
+                                             layer.rows)
+        assert rel_fro(to_np_f32(yb), to_np_f32(ya)) <= 3e-2
