@@ -7,8 +7,9 @@
 // groups are runs of 32 * i rows, so a 32-row block never straddles a group or a section.
 //
 // Kernel: lane = output column (a packed row is N contiguous words: every weight load is a full 128-byte line), warp =
-// k-slice of the column strip, eight warps per CTA whose partial sums meet in shared memory -- y is written once, no
-// atomics, deterministic.  A block of 32 codes costs b coalesced word loads; a code becomes the fp16 number 1024 + q with
+// k-slice of the column strip, eight warps per CTA and up to four CTAs of a thread-block CLUSTER per strip (so that a
+// 4096-column layer puts 512 CTAs on the 148 SMs instead of 128): the warps' partial sums meet in shared memory, the
+// CTAs' through distributed shared memory in rank order -- y is written once, no atomics, deterministic.  A block of 32 codes costs b coalesced word loads; a code becomes the fp16 number 1024 + q with
 // one funnel shift + one LOP3 ((v & mask) | 0x6400) and is multiplied with the activation by the mixed-precision FMA
 // (fma.rn.f32.f16: exact product, fp32 accumulation).  The group affine is factored out:
 //     y += s * sum((1024 + q) x) - (1024 s + z) * sum(x)
@@ -16,6 +17,7 @@
 // Replaces gemm_half_q_half_kernel (exl2/q_gemm_kernel.cuh:90-549; 64-row CTAs, K/64 half2 atomics per output, fp16
 // accumulation) and, in this repo's round 1, a dequantise + cuBLAS pair.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace b200bit {
 
@@ -98,8 +100,11 @@ __global__ void __launch_bounds__(EX_WARPS * 32) exl2_gemv_kernel(const Exl2Para
 #pragma unroll
     for (int m = 0; m < MB; ++m) yacc[m] = 0.f;
 
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
     const int blocks_total = p.K / 32;
-    const int b_lo = warp * p.blocks_per_warp;
+    const int b_lo = (crank * EX_WARPS + warp) * p.blocks_per_warp;
     const int b_hi = min(blocks_total, b_lo + p.blocks_per_warp);
     for (int c0 = b_lo; c0 < b_hi; c0 += EX_CHUNK / 32) {
         const int nblk = min(EX_CHUNK / 32, b_hi - c0);
@@ -146,28 +151,55 @@ __global__ void __launch_bounds__(EX_WARPS * 32) exl2_gemv_kernel(const Exl2Para
             }
         }
     }
-    // ---- the eight k-slices meet in shared memory, fixed order ----
+    // ---- the eight k-slices of the CTA meet in shared memory, then the CTAs of the cluster in rank order ----
 #pragma unroll
     for (int m = 0; m < MB; ++m) red[(warp * MB + m) * 32 + lane] = yacc[m];
     __syncthreads();
+    float* cta_sum = red + EX_WARPS * MB * 32;             // [MB][32]
     for (int i = threadIdx.x; i < MB * 32; i += EX_WARPS * 32) {
         const int m = i / 32, l = i % 32;
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < EX_WARPS; ++w) t += red[(w * MB + m) * 32 + l];
-        const int col = blockIdx.x * 32 + l;
-        if (col < p.N && m0 + m < p.M) p.y[size_t(m0 + m) * p.N + col] = __float2half_rn(t);
+        cta_sum[i] = t;
     }
+    cluster.sync();
+    if (crank == 0) {
+        for (int i = threadIdx.x; i < MB * 32; i += EX_WARPS * 32) {
+            const int m = i / 32, l = i % 32;
+            float t = cta_sum[i];
+            for (int r = 1; r < csize; ++r) t += cluster.map_shared_rank(cta_sum, r)[i];
+            const int col = blockIdx.x * 32 + l;
+            if (col < p.N && m0 + m < p.M) p.y[size_t(m0 + m) * p.N + col] = __float2half_rn(t);
+        }
+    }
+    cluster.sync();          // the other CTAs' shared memory stays alive until rank 0 has read it
 }
 
 template <int MB>
-static int launch_exl2(const Exl2Params& p, cudaStream_t st) {
-    const size_t smem = size_t(EX_WARPS) * MB * (EX_CHUNK * sizeof(__half) + 8 * sizeof(float)) + size_t(EX_WARPS) * MB * 32 * sizeof(float);
+static int launch_exl2(Exl2Params p, cudaStream_t st) {
+    const size_t smem = size_t(EX_WARPS) * MB * (EX_CHUNK * sizeof(__half) + 8 * sizeof(float)) +
+                        size_t(EX_WARPS + 1) * MB * 32 * sizeof(float);
     auto kern = exl2_gemv_kernel<MB>;
     if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    dim3 grid((p.N + 31) / 32, (p.M + MB - 1) / MB);
-    kern<<<grid, EX_WARPS * 32, smem, st>>>(p);
-    B200_CUDA_OK(cudaGetLastError());
+    // k-slices: 8 warps x cluster size; enough CTAs for ~3 per SM, at least 2 blocks of 32 rows per warp
+    const int blocks = p.K / 32, strips = (p.N + 31) / 32, mchunks = (p.M + MB - 1) / MB;
+    int csize = 1;
+    while (csize < 4 && strips * mchunks * csize < 3 * sm_count() && blocks >= 2 * EX_WARPS * csize * 2) csize *= 2;
+    p.blocks_per_warp = (blocks + EX_WARPS * csize - 1) / (EX_WARPS * csize);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(strips, mchunks, csize);
+    cfg.blockDim = dim3(EX_WARPS * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = csize;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
     return B200BIT_OK;
 }
 
@@ -203,7 +235,6 @@ extern "C" int b200bit_exl2_forward(const void* x, const int32_t* qweight, const
     p.x = reinterpret_cast<const __half*>(x);
     p.y = reinterpret_cast<__half*>(y);
     p.M = M; p.K = K; p.N = N;
-    p.blocks_per_warp = (K / 32 + EX_WARPS - 1) / EX_WARPS;
     if (M == 1) return launch_exl2<1>(p, st);
     if (M == 2) return launch_exl2<2>(p, st);
     if (M <= 4) return launch_exl2<4>(p, st);

@@ -34,6 +34,37 @@ template <> struct El<B200BIT_BF16> {
     __device__ static float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 };
 
+// eight consecutive elements as floats: 128-bit accesses (one for the 16-bit types, two for fp32)
+template <int DT>
+__device__ __forceinline__ void load8(const void* p, size_t i, float (&v)[8]) {
+    if constexpr (DT == B200BIT_F32) {
+        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+        const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p) + i);
+        const uint32_t r[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[2 * q] = cvt16_lo<DT == B200BIT_BF16>(r[q]);
+            v[2 * q + 1] = cvt16_hi<DT == B200BIT_BF16>(r[q]);
+        }
+    }
+}
+template <int DT>
+__device__ __forceinline__ void store8(void* p, size_t i, const float (&v)[8]) {
+    if constexpr (DT == B200BIT_F32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        uint32_t r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            r[q] = uint32_t(f32_to_16<DT == B200BIT_BF16>(v[2 * q])) | (uint32_t(f32_to_16<DT == B200BIT_BF16>(v[2 * q + 1])) << 16);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p) + i) = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+}
+
 __device__ __forceinline__ int group_of(const int32_t* g_idx, int k, int gs) { return g_idx ? g_idx[k] : k / gs; }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -76,6 +107,53 @@ __global__ void __launch_bounds__(256) mpq_dequant_kernel(const uint32_t* __rest
         else v = El<DT>::rnd(__fsub_rn(El<DT>::rnd(__fmul_rn(q, s)), z));
         const int ko = perm ? int(perm[k]) : k;
         El<DT>::st(out, size_t(ko) * N + n, v);
+    }
+}
+
+// Vector flavour (N % 8 == 0): a thread owns eight consecutive columns of one packed row -- two 128-bit loads of packed
+// words, 128-bit loads of the group's scales / zeros, one 128-bit store per output row (two for fp32).  Same arithmetic,
+// same roundings as the scalar kernel above (which stays for odd N).
+template <int DT>
+__global__ void __launch_bounds__(128) mpq_dequant_vec_kernel(const uint32_t* __restrict__ qw, const void* __restrict__ scales,
+                                                              const void* __restrict__ zeros, const int32_t* __restrict__ g_idx,
+                                                              void* __restrict__ out, int K, int N, int G, int w_bit, int asym,
+                                                              int fused, const uint16_t* __restrict__ perm) {
+    const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int r = blockIdx.y;
+    if (n0 >= N) return;
+    const int nb = 32 / w_bit, gs = K / G;
+    const uint32_t mask = (1u << w_bit) - 1u;
+    const uint4 wa = ldg_stream_v4(qw + size_t(r) * N + n0), wb = ldg_stream_v4(qw + size_t(r) * N + n0 + 4);
+    const uint32_t w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+    int g_prev = -1;
+    float s[8], z[8];
+    for (int j = 0; j < nb; ++j) {
+        const int k = r * nb + j;
+        const int g = group_of(g_idx, k, gs);
+        if (g != g_prev) {
+            load8<DT>(scales, size_t(g) * N + n0, s);
+            if (asym) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int n = n0 + c;
+                    const uint32_t zw = reinterpret_cast<const uint32_t*>(zeros)[size_t(g) * (N / nb) + n / nb];
+                    z[c] = float(((zw >> ((n % nb) * w_bit)) & mask) + 1u);
+                }
+            } else {
+                load8<DT>(zeros, size_t(g) * N + n0, z);
+            }
+            g_prev = g;
+        }
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float q = float((w[c] >> (j * w_bit)) & mask);
+            if (asym) v[c] = __fmul_rn(s[c], __fsub_rn(q, z[c]));
+            else if (fused) v[c] = fmaf(s[c], q, -z[c]);
+            else v[c] = __fsub_rn(El<DT>::rnd(__fmul_rn(q, s[c])), z[c]);
+        }
+        const int ko = perm ? int(perm[k]) : k;
+        store8<DT>(out, size_t(ko) * N + n0, v);           // the store rounds to DT (the last rnd of every formula)
     }
 }
 
@@ -127,6 +205,58 @@ __global__ void __launch_bounds__(256) mpq_pack_kernel(const void* __restrict__ 
         word |= (uint32_t(c) & mask) << (j * w_bit);
     }
     out[size_t(r) * N + n] = word;
+}
+
+// Vector flavour of the pack kernel (N % 8 == 0): eight columns per thread, 128-bit loads of the weight rows and of
+// the group parameters, two 128-bit stores of packed words.
+template <int DT, int WT>
+__global__ void __launch_bounds__(128) mpq_pack_vec_kernel(const void* __restrict__ weight, const void* __restrict__ scales,
+                                                           const void* __restrict__ zeros, const int32_t* __restrict__ g_idx,
+                                                           const int16_t* __restrict__ perm, uint32_t* __restrict__ out,
+                                                           int K, int N, int G, int w_bit, int asym, int zeros_unpacked) {
+    const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int r = blockIdx.y;
+    if (n0 >= N) return;
+    constexpr int CT = (WT == B200BIT_F32) ? B200BIT_F32 : DT;
+    const int nb = 32 / w_bit, gs = K / G;
+    const uint32_t mask = (1u << w_bit) - 1u;
+    const float maxq = float(mask);
+    uint32_t word[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    int g_prev = -1;
+    float s[8], z[8];
+    for (int j = 0; j < nb; ++j) {
+        const int k = r * nb + j;
+        const int g = group_of(g_idx, k, gs);
+        if (g != g_prev) {
+            load8<DT>(scales, size_t(g) * N + n0, s);
+            if (asym && !zeros_unpacked) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int n = n0 + c;
+                    const uint32_t zw = reinterpret_cast<const uint32_t*>(zeros)[size_t(g) * (N / nb) + n / nb];
+                    z[c] = float(((zw >> ((n % nb) * w_bit)) & mask) + 1u);
+                }
+            } else {
+                load8<DT>(zeros, size_t(g) * N + n0, z);
+            }
+            g_prev = g;
+        }
+        const int ks = perm ? int(uint16_t(perm[k])) : k;
+        float wv[8];
+        load8<WT>(weight, size_t(ks) * N + n0, wv);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float t;
+            if (asym) t = El<CT>::rnd(__fadd_rn(El<CT>::rnd(__fdiv_rn(wv[c], s[c])), z[c]));
+            else t = El<CT>::rnd(__fdiv_rn(El<CT>::rnd(__fadd_rn(wv[c], z[c])), s[c]));
+            float cq = rintf(t);
+            cq = fminf(fmaxf(cq, 0.f), maxq);
+            if (!(cq == cq)) cq = 0.f;
+            word[c] |= (uint32_t(cq) & mask) << (j * w_bit);
+        }
+    }
+    *reinterpret_cast<uint4*>(out + size_t(r) * N + n0) = make_uint4(word[0], word[1], word[2], word[3]);
+    *reinterpret_cast<uint4*>(out + size_t(r) * N + n0 + 4) = make_uint4(word[4], word[5], word[6], word[7]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -278,6 +408,16 @@ int b200bit_mpq_dequant(const int32_t* qweight, const void* scales, const void* 
     const int nb = 32 / w_bit;
     dim3 grid((N + 255) / 256, K / nb);
     const uint32_t* q = reinterpret_cast<const uint32_t*>(qweight);
+    const bool aligned = (reinterpret_cast<uintptr_t>(qweight) | reinterpret_cast<uintptr_t>(scales) | reinterpret_cast<uintptr_t>(zeros) |
+                          reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+    if (N % 8 == 0 && aligned) {
+        dim3 vgrid((N / 8 + 127) / 128, K / nb);
+        if (dtype == B200BIT_F32) mpq_dequant_vec_kernel<B200BIT_F32><<<vgrid, 128, 0, st>>>(q, scales, zeros, g_idx, out, K, N, G, w_bit, asym, fused, perm);
+        else if (dtype == B200BIT_F16) mpq_dequant_vec_kernel<B200BIT_F16><<<vgrid, 128, 0, st>>>(q, scales, zeros, g_idx, out, K, N, G, w_bit, asym, fused, perm);
+        else mpq_dequant_vec_kernel<B200BIT_BF16><<<vgrid, 128, 0, st>>>(q, scales, zeros, g_idx, out, K, N, G, w_bit, asym, fused, perm);
+        B200_CUDA_OK(cudaGetLastError());
+        return B200BIT_OK;
+    }
     if (dtype == B200BIT_F32) mpq_dequant_kernel<B200BIT_F32><<<grid, 256, 0, st>>>(q, scales, zeros, g_idx, out, K, N, G, w_bit, asym, fused, perm);
     else if (dtype == B200BIT_F16) mpq_dequant_kernel<B200BIT_F16><<<grid, 256, 0, st>>>(q, scales, zeros, g_idx, out, K, N, G, w_bit, asym, fused, perm);
     else mpq_dequant_kernel<B200BIT_BF16><<<grid, 256, 0, st>>>(q, scales, zeros, g_idx, out, K, N, G, w_bit, asym, fused, perm);
@@ -326,6 +466,20 @@ int b200bit_mpq_pack_weight(const void* weight, const void* scales, const void* 
     dim3 grid((N + 255) / 256, K / nb);
     uint32_t* o = reinterpret_cast<uint32_t*>(qweight_out);
     const bool wf32 = weight_dtype == B200BIT_F32;
+    const bool aligned = (reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(scales) | reinterpret_cast<uintptr_t>(zeros) |
+                          reinterpret_cast<uintptr_t>(qweight_out)) % 16 == 0;
+    if (N % 8 == 0 && aligned) {
+        dim3 vgrid((N / 8 + 127) / 128, K / nb);
+#define B200_PACK_VEC(DT_, WT_) mpq_pack_vec_kernel<DT_, WT_><<<vgrid, 128, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked)
+        if (dtype == B200BIT_F32) B200_PACK_VEC(B200BIT_F32, B200BIT_F32);
+        else if (dtype == B200BIT_F16 && wf32) B200_PACK_VEC(B200BIT_F16, B200BIT_F32);
+        else if (dtype == B200BIT_F16) B200_PACK_VEC(B200BIT_F16, B200BIT_F16);
+        else if (wf32) B200_PACK_VEC(B200BIT_BF16, B200BIT_F32);
+        else B200_PACK_VEC(B200BIT_BF16, B200BIT_BF16);
+#undef B200_PACK_VEC
+        B200_CUDA_OK(cudaGetLastError());
+        return B200BIT_OK;
+    }
     if (dtype == B200BIT_F32) mpq_pack_kernel<B200BIT_F32, B200BIT_F32><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);
     else if (dtype == B200BIT_F16 && wf32) mpq_pack_kernel<B200BIT_F16, B200BIT_F32><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);
     else if (dtype == B200BIT_F16) mpq_pack_kernel<B200BIT_F16, B200BIT_F16><<<grid, 256, 0, st>>>(weight, scales, zeros, g_idx, perm, o, K, N, G, w_bit, asym, zeros_unpacked);

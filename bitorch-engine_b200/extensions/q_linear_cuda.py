@@ -1,8 +1,25 @@
 """Twin of the reference pybind module `q_linear_cuda`
 (bitorch_engine/layers/qlinear/nbit/cuda/q_linear_cuda.cpp:357-369)."""
+import contextlib
+
 import torch
 
 from .. import _cabi
+from .. import decode_chain
+
+_NULL_CTX = contextlib.nullcontext()
+_ws_bytes = {}
+
+
+def _on_device(device):
+    """device guard only when the tensor does not live on the current device (the guard costs ~4 us per call, as much as
+    a whole decode kernel; the reference pays an OptionalCUDAGuard in C++, mpq_linear_cuda_kernel.cu:612)"""
+    return _NULL_CTX if device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+
+def _raw_stream(device):
+    return torch._C._cuda_getCurrentRawStream(device.index)
+
 
 def _check_cuda(t, name):
     # reference: CHECK_CUDA -> AT_ASSERTM -> RuntimeError (q_linear_cuda.cpp:255-256)
@@ -63,6 +80,7 @@ def _input_ready(x, stream):
 
 
 MPQ_FUSED_MAX_ROWS = 32
+GRAD_INPUT_FUSED_MAX_ROWS = 4
 
 
 def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False):
@@ -87,7 +105,6 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         raise ValueError(f"scales dtype {scales.dtype} must match x dtype {x.dtype}")
     if M == 0:
         return torch.empty((0, N), dtype=x.dtype, device=x.device)
-    from .. import decode_chain
     rec = decode_chain.recording()
     if rec is not None:
         # DecodeChain.capture: the call becomes a node of the chain (nothing is launched here)
@@ -106,10 +123,14 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
     lib = _cabi.lib()
     trivial = _gidx_is_trivial(g_idx, K, G)
     y = torch.empty((M, N), dtype=x.dtype, device=x.device)
-    with torch.cuda.device(x.device):
-        stream = torch.cuda.current_stream().cuda_stream
-        need = lib.b200bit_mpq_forward_workspace_bytes(M, K, N, w_bit)
-        ws = _cabi.workspace(x.device, stream, need)
+    device = x.device
+    with _on_device(device):
+        stream = _raw_stream(device)
+        key = (M, K, N, w_bit)
+        need = _ws_bytes.get(key)
+        if need is None:
+            need = _ws_bytes[key] = lib.b200bit_mpq_forward_workspace_bytes(M, K, N, w_bit)
+        ws = _cabi.workspace(device, stream, need)
         flags = 0
         if pdl:
             flags = _cabi.FLAG_PDL
@@ -120,7 +141,8 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
             None if trivial else g_idx.contiguous().data_ptr(), y.data_ptr(),
             M, K, N, G, w_bit, int(bool(asym)), _cabi.dtype_code(x.dtype),
             ws.data_ptr(), ws.numel(), flags, stream)
-    _cabi.check(rc)
+    if rc:
+        _cabi.check(rc)
     return y
 
 
@@ -140,6 +162,12 @@ def mpq_grad_input(qweight, scales, zeros, g_idx, output_gradient, a_bit, w_bit,
     G = scales.shape[0]
     if scales.dtype != dy.dtype:
         raise ValueError(f"scales dtype {scales.dtype} must match output_gradient dtype {dy.dtype}")
+    if M > GRAD_INPUT_FUSED_MAX_ROWS and dy.dtype != torch.float32:
+        # measured on B200 (profiles/configs_r02.json): the warp-per-packed-row kernel re-reads W once per 4 rows of dy and
+        # needs 190 - 530 us at 32 rows; dequantise once (one kernel) + the dense GEMM needs ~55 us there and runs at
+        # tensor-core speed for the training shapes (M = 2048).  The reference's own kernel (back_quant_mm_kernel,
+        # mpq_linear_cuda_kernel.cu:920-983) is slower than either.
+        return torch.matmul(dy, mpq_dequant(qweight, scales, zeros, g_idx, w_bit, asym).t())
     trivial = _gidx_is_trivial(g_idx, K, G)
     dx = torch.empty((M, K), dtype=dy.dtype, device=dy.device)
     if M == 0:
@@ -329,10 +357,11 @@ def mbwq_exl2_forward(x, qweight, scales, zeros, q_perm, q_group_map, rows, use_
         return y
     rows6 = (ctypes.c_int * 6)(*[int(r) for r in rows[:6]])
     perm = None if (q_perm is None or _perm_is_identity(q_perm, K)) else q_perm.contiguous()
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         rc = _cabi.lib().b200bit_exl2_forward(x.contiguous().data_ptr(), qweight.contiguous().data_ptr(),
                                               scales.contiguous().data_ptr(), zeros.contiguous().data_ptr(), _ptr(perm),
                                               q_group_map.contiguous().data_ptr(), y.data_ptr(), M, K, N, rows6,
-                                              torch.cuda.current_stream().cuda_stream)
-    _cabi.check(rc)
+                                              _raw_stream(x.device))
+    if rc:
+        _cabi.check(rc)
     return y

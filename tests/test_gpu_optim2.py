@@ -125,7 +125,7 @@ def test_diodemix_end_to_end_on_stock_torch():
     for l in (used, unused):
         l.prepare_params()
         l.train()
-    mpq = MPQLinearCuda(256, 256, w_bit=4, group_size=128, dq_group_size=128, use_gba_quant=False, dtype=torch.half).cuda()
+    mpq = MPQLinearCuda(128, 256, w_bit=4, group_size=128, dq_group_size=128, use_gba_quant=False, dtype=torch.half).cuda()
     mpq.qweight.data = torch.randint(-2 ** 31, 2 ** 31 - 1, mpq.qweight.shape, dtype=torch.int32, device="cuda")
     mpq.scales.fill_(0.01)
     mpq.prepare_params()
