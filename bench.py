@@ -188,6 +188,89 @@ def build_model(device, seed):
     return layers
 
 
+LLAMA3_8B = dict(hidden=4096, inter=14336, kv=1024, layers=32)
+
+
+def run_llama3(args, rank, world, dev):
+    """BASELINE config #5: Llama-3-8B 4-bit (g128) linear layers, synthetic 512-token prompts, one independent stream per
+    GPU.  Step = one prompt: prefill (M = 512 through the 224 linears: tcgen05 batched kernel / dequantise + dense GEMM)
+    followed by 16 decoded tokens (decode chain).  Attention, norms and SiLU are identity stand-ins as in the headline
+    (k / v are 1024 wide with GQA: o reads q's output).  value = prefill tokens/s over all ranks; decode tokens/s beside it."""
+    import torch
+    import torch.distributed as dist
+    from bitorch_engine_b200.extensions import q_linear_cuda
+    from bitorch_engine_b200.decode_chain import DecodeChain
+    c = LLAMA3_8B
+    h, i, kv = c["hidden"], c["inter"], c["kv"]
+    shapes = [("q", h, h), ("k", h, kv), ("v", h, kv), ("o", h, h), ("gate", h, i), ("up", h, i), ("down", i, h)]
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    layers = []
+    for li in range(c["layers"]):
+        for name, K, N in shapes:
+            qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (K // 8, N), dtype=torch.int32, device=dev, generator=g)
+            s0 = 1.0 / (K ** 0.5 * 4.61)
+            sc = (s0 * (0.75 + 0.5 * torch.rand((K // GROUP, N), device=dev, generator=g))).half()
+            layers.append((name, K, N, qw, sc, (sc.float() * 7.5).half(), torch.arange(K, dtype=torch.int32, device=dev) // GROUP))
+    PROMPT, NEW = 512, 16
+
+    def forward(hid):
+        for li in range(c["layers"]):
+            lq, lk, lv, lo, lg, lu, ld = layers[li * 7:(li + 1) * 7]
+            f = lambda x, l: q_linear_cuda.mpq_forward(x, l[3], l[4], l[5], l[6], 16, W_BIT, False)
+            q, k, v = f(hid, lq), f(hid, lk), f(hid, lv)
+            o = f(q, lo)
+            gate, up = f(o, lg), f(o, lu)
+            hid = f(up, ld)
+        return hid
+
+    x_prompt = torch.randn((PROMPT, h), device=dev, generator=g).half()      # embedded prompt (random token ids, seed 7 + rank)
+    x_tok = torch.randn((1, h), device=dev, generator=g).half()
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        forward(x_prompt)
+        chain = DecodeChain.capture(lambda: forward(x_tok))
+        chain.launch(); chain.check()
+        stream.synchronize()
+
+        def step():
+            forward(x_prompt)
+            for _ in range(NEW):
+                chain.launch()
+        for _ in range(max(args.warmup, 3)):
+            step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = min(args.steps, 20)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    ms_prefill = ms_decode = 0.0
+    with torch.cuda.stream(stream):
+        for _ in range(steps):
+            e0.record(stream); forward(x_prompt); e1.record(stream)
+            for _ in range(NEW):
+                chain.launch()
+            e2.record(stream)
+            stream.synchronize()
+            ms_prefill += e0.elapsed_time(e1); ms_decode += e1.elapsed_time(e2)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_prefill, ms_decode = max_over_ranks([ms_prefill, ms_decode], world, dev)
+    if rank == 0:
+        flops = 2 * PROMPT * sum(K * N for _, K, N, *_ in layers)
+        line = {"metric": "llama3_8b_w4g128_linear_prefill512_tokens_per_s", "value": world * steps * PROMPT / (ms_prefill / 1e3),
+                "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": (ms_prefill + ms_decode) / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16", "data": "synthetic",
+                "config": {"workload": "llama3_8b_linear_layers_w4_g128_sym: 512-token prefill + 16 decoded tokens per stream",
+                           "streams": world, "parallelism": f"replicas x{world}"},
+                "prefill": {"ms_per_prompt": ms_prefill / steps, "TFLOPs": flops / (ms_prefill / steps) / 1e9},
+                "decode": {"tokens_per_s": world * steps * NEW / (ms_decode / 1e3), "ms_per_token": ms_decode / steps / NEW},
+                "gpu_launches": steps * (len(layers) + NEW)}
+        print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -196,6 +279,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("B200BIT_PDL", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="llama7b_decode", choices=["llama7b_decode", "llama3_8b_prefill512"],
+                    help="llama7b_decode = the headline (BASELINE.json metric / configs[1]); llama3_8b_prefill512 = config #5: "
+                         "Llama-3-8B linear layers, a 512-token prompt per stream (prefill) + decode, one stream per GPU")
     ap.add_argument("--chain", type=int, default=int(os.environ.get("B200BIT_CHAIN", "1")),
                     help="1: the token's 224 layer calls recorded into ONE decode-chain launch (DecodeChain.capture); "
                          "0: one launch per layer (programmatic dependent launch), as in round 1")
@@ -242,6 +328,12 @@ def main():
     if tune:
         L, wps, sk = (int(v) for v in tune.split(","))
         _cabi.check(_cabi.lib().b200bit_set_gemv_tuning(L, wps, sk))
+
+    if args.workload == "llama3_8b_prefill512":
+        rc = run_llama3(args, rank, world, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return rc
 
     layers = build_model(dev, seed=rank_seed(rank))
     h, inter = LLAMA7B["hidden"], LLAMA7B["inter"]

@@ -6,7 +6,6 @@
 #include "mpq_gemv.cuh"
 #include "mpq_mma.cuh"
 #include "mpq_stream.cuh"
-#include "mpq_umma.cuh"
 #include "mpq_pipe.cuh"
 #include "mpq_pipe_mma.cuh"
 #include "mpq_imma.cuh"
@@ -46,7 +45,7 @@ int sm_count() {
 // process-wide tuning override for sweeps (0 = heuristic); set through b200bit_set_gemv_tuning()
 static int g_tune_L = 0, g_tune_warps = 0, g_tune_splitk = 0;
 // 0 = auto, 1 = CUDA-core FHFMA GEMV, 2 = mma.sync small-batch kernel, 3 = general fallback,
-// 4 = TMA-streamed small-batch kernel, 5 = tcgen05 batched kernel, 6 = cross-kernel pipelined decode GEMV (mpq_pipe.cuh),
+// 4 = TMA-streamed small-batch kernel, 5 = tcgen05 batched kernel (mpq_tc.cu, more than 32 rows), 6 = cross-kernel pipelined decode GEMV (mpq_pipe.cuh),
 // 7 = persistent integer-tensor-pipe decode GEMV (mpq_imma.cuh)
 static int g_path = 0;
 // in auto mode, does M == 1 go to the tensor kernel (1) or stay on the CUDA-core GEMV (0)?
@@ -461,60 +460,6 @@ static StreamPlan plan_stream(int M, int K, int N, int G, int w_bit, int asym, i
     return pl;
 }
 
-struct UmmaPlan {
-    bool ok;
-    int FJ2, MB, ngr, rpr, rpr_shift, strips, rps, steps, grid, S;
-    size_t smem, img_bytes, xsum_bytes;
-};
-
-// tcgen05 batched kernel (mpq_umma.cuh): f16, 4-bit, contiguous groups of 64 / 128 / multiples of 256, <= 32 rows per pass
-static UmmaPlan plan_umma(int M, int K, int N, int G, int w_bit, int asym, int dtype, bool trivial_gidx) {
-    UmmaPlan pl{};
-    pl.ok = false;
-    if (!trivial_gidx || dtype != B200BIT_F16 || w_bit != 4) return pl;
-    const int nb = 8;
-    if (N % 32 != 0 || K % (nb * 32) != 0 || K % G != 0) return pl;
-    if (asym && N % (4 * nb) != 0) return pl;
-    const int gs = K / G;
-    if (gs % nb != 0) return pl;
-    const int rpg = gs / nb;
-    if (rpg == 8 || rpg == 16) {
-        pl.FJ2 = rpg / 8; pl.ngr = 32 / rpg; pl.rpr = 1; pl.rpr_shift = 0;
-    } else if (rpg % 32 == 0) {
-        pl.FJ2 = 4; pl.ngr = 1; pl.rpr = rpg / 32; pl.rpr_shift = -1;
-        for (int sh = 0; sh < 30; ++sh) if ((1 << sh) == pl.rpr) pl.rpr_shift = sh;
-    } else {
-        return pl;
-    }
-    pl.strips = N / 32;
-    pl.rps = (K / nb) / 32;
-    if (pl.rps < 4) return pl;
-    pl.steps = (pl.rps + 3) / 4;
-    int grid = sm_count();
-    if (grid > pl.strips) grid = pl.strips;
-    pl.grid = grid;
-    const int strips_max = (pl.strips + grid - 1) / grid;
-    const int mm = M < 32 ? M : 32;
-    pl.MB = mm <= 4 ? 4 : mm <= 8 ? 8 : mm <= 16 ? 16 : 32;
-    if (g_tune_splitk == 4 || g_tune_splitk == 8 || g_tune_splitk == 16 || g_tune_splitk == 32)       // sweep hook
-        if (g_tune_splitk >= mm) pl.MB = g_tune_splitk;
-    const int nmma = 4 * pl.MB, gps = 4 / pl.FJ2;
-    pl.img_bytes = size_t(pl.steps) * nmma * 512;
-    pl.xsum_bytes = (size_t(pl.MB) * 4 * pl.steps * gps * 4 + 127) & ~size_t(127);
-    const size_t fixed = size_t(UM_BSTAGES) * nmma * 512 + ((size_t(pl.MB) * 4 * pl.steps * gps + 3) & ~size_t(3)) * 4 +
-                         size_t(4) * pl.MB * 32 * 4 + 1024;
-    int S = g_tune_warps > 0 ? g_tune_warps : 5;
-    const int total = strips_max * pl.steps;
-    if (S > total + 1) S = total + 1;
-    if (S < 2) S = 2;
-    for (; S >= 2; --S) {
-        pl.S = S;
-        pl.smem = fixed + size_t(S) * 4 * (UM_TILE + UM_SZ) + size_t(8 * S + 40) * 8;
-        if (pl.smem <= 225 * 1024) { pl.ok = true; break; }
-    }
-    return pl;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // cross-kernel pipelined decode GEMV (mpq_pipe.cuh): M == 1, f16 / bf16, contiguous groups
 // ---------------------------------------------------------------------------------------------------------------
@@ -835,46 +780,13 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
         return rc;
     }
     chain_invalidate(stream);      // every other kernel triggers its dependents before its own dependency wait
+    // ---- more than 32 rows: tcgen05 batched kernel (mpq_tc.cu), one pass over the packed matrix ----
+    if (M > 32 && (g_path == 0 || g_path == 5) && trivial && w_bit == 4 && dtype == B200BIT_F16 && K % 64 == 0 && N % 8 == 0 &&
+        K % G == 0 && (K / G) % 32 == 0 && ((K / G) & (K / G - 1)) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        size_t(G) * (asym ? 320 : 512) <= size_t(160) * 1024)
+        return b200bit_mpq_forward_tc(x, qweight, scales, zeros, y, M, K, N, G, w_bit, asym, dtype, stream_);
     // ---- path selection: TMA-streamed tensor kernel (f16, M <= 32) > mma.sync kernel > CUDA-core GEMV > general ----
     // auto: M == 1 -> CUDA-core FHFMA GEMV (fastest measured at batch 1, profiles/r1_*); 2 <= M: TMA-streamed tensor kernel
-    const UmmaPlan up = (g_path == 5) ? plan_umma(M, K, N, G, w_bit, asym, dtype, trivial) : UmmaPlan{};
-    if (up.ok && workspace && workspace_bytes >= size_t(B200BIT_WS_TICKET_BYTES) + up.img_bytes + up.xsum_bytes) {
-        CUtensorMap tw, ts, tz;
-        int rc = make_map_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_UINT32, qweight, uint64_t(N), uint64_t(K / nb), uint64_t(N) * 4,
-                             32, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
-        if (rc != B200BIT_OK) return rc;
-        rc = make_map_2d(&ts, CU_TENSOR_MAP_DATA_TYPE_UINT16, scales, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
-                         uint32_t(up.ngr), CU_TENSOR_MAP_SWIZZLE_NONE);
-        if (rc != B200BIT_OK) return rc;
-        if (asym)
-            rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT32, zeros, uint64_t(N / nb), uint64_t(G),
-                             uint64_t(N / nb) * 4, uint32_t(32 / nb), uint32_t(up.ngr), CU_TENSOR_MAP_SWIZZLE_NONE);
-        else
-            rc = make_map_2d(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT16, zeros, uint64_t(N), uint64_t(G), uint64_t(N) * 2, 32,
-                             uint32_t(up.ngr), CU_TENSOR_MAP_SWIZZLE_NONE);
-        if (rc != B200BIT_OK) return rc;
-        unsigned char* img = reinterpret_cast<unsigned char*>(workspace) + B200BIT_WS_TICKET_BYTES;
-        float* xsum = reinterpret_cast<float*>(img + up.img_bytes);
-        for (int m0 = 0; m0 < M; m0 += up.MB) {
-            const int mc = (M - m0) < up.MB ? (M - m0) : up.MB;
-            UmmaPrepParams pp{};
-            pp.x = reinterpret_cast<const uint16_t*>(x) + size_t(m0) * K;
-            pp.bimg = img; pp.xsum = xsum; pp.M = mc; pp.K = K; pp.MB = up.MB; pp.rps = up.rps; pp.steps = up.steps;
-            pp.fj2 = up.FJ2;
-            rc = launch_umma_prepare(pp, flags, stream);
-            if (rc != B200BIT_OK) return rc;
-            UmmaParams p{};
-            p.bimg = img; p.xsum = xsum;
-            p.y = reinterpret_cast<uint16_t*>(y) + size_t(m0) * N;
-            p.M = mc; p.K = K; p.N = N; p.strips = up.strips; p.rps = up.rps; p.steps = up.steps; p.ngr = up.ngr;
-            p.rpr = up.rpr; p.rpr_shift = up.rpr_shift; p.asym = asym; p.S = up.S; p.trace = g_trace;
-            UmmaLaunch l{};
-            l.FJ2 = up.FJ2; l.MB = up.MB; l.grid = up.grid; l.smem = up.smem; l.flags = flags; l.stream = stream;
-            rc = launch_umma(tw, ts, tz, p, l);
-            if (rc != B200BIT_OK) return rc;
-        }
-        return B200BIT_OK;
-    }
     const StreamPlan sp = (g_path == 4 || (g_path == 0 && M >= 2)) ? plan_stream(M, K, N, G, w_bit, asym, dtype, trivial)
                                                                  : StreamPlan{};
     if (sp.ok) {
@@ -901,8 +813,7 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
             p.y = reinterpret_cast<uint16_t*>(y) + size_t(m0) * N;
             p.zero_page = reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(workspace) + B200BIT_WS_ZERO_OFFSET);
             p.M = mc; p.K = K; p.N = N; p.strips = sp.strips; p.rps = sp.rps; p.ngr = sp.ngr; p.rpr = sp.rpr;
-            p.rpr_shift = sp.rpr_shift; p.asym = asym; p.S = sp.S; p.maxseg = sp.maxseg; p.trace = g_trace; p.debug_no_x = (g_tune_L == 16);
-            { static const int pm = getenv("B200BIT_STREAM_PRODUCER") ? atoi(getenv("B200BIT_STREAM_PRODUCER")) : 0; p.producer_mode = pm; }
+            p.rpr_shift = sp.rpr_shift; p.asym = asym; p.S = sp.S; p.maxseg = sp.maxseg; p.trace = g_trace;
             StreamLaunch l{};
             l.MT = (mc + 7) / 8; l.FJ = sp.FJ; l.warps = sp.warps; l.grid = sp.grid; l.xs = sp.xs;
             l.smem = sp.smem; l.flags = flags; l.stream = stream;

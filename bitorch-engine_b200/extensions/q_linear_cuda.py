@@ -80,6 +80,7 @@ def _input_ready(x, stream):
 
 
 MPQ_FUSED_MAX_ROWS = 32
+TC_MAX_ROWS = 1 << 30      # measured on B200 (profiles/r2_21_tc_kernel_vs_dequant_cublas.jsonl): ahead of dequantise + cuBLAS at every M
 GRAD_INPUT_FUSED_MAX_ROWS = 4
 
 
@@ -112,9 +113,24 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
             raise NotImplementedError("DecodeChain: act-order g_idx is not supported inside a chain")
         return rec.add(x, qweight, scales, zeros, w_bit, asym)
     if M > MPQ_FUSED_MAX_ROWS and x.dtype != torch.float32:
-        # large batches (prefill, training): dequantise ONCE (one kernel, bit-identical to unpack_qweight) + dense GEMM --
-        # the switch the reference makes at the same point (mpq_layer.py:59-63); one pass over the packed matrix instead of
-        # re-streaming it per 32-row group
+        # large batches (prefill, training).  Up to TC_MAX_ROWS rows: the tcgen05 kernel (csrc/mpq_tc.cu) -- weights
+        # dequantised straight into tensor memory, one pass over the packed matrix, no fp16 copy of W in HBM.  Beyond that
+        # (or for shapes it does not cover): dequantise ONCE (one kernel, bit-identical to unpack_qweight) + dense GEMM, the
+        # switch the reference makes at 32 rows (mpq_layer.py:59-63).
+        gs = K // G if G and K % G == 0 else 0
+        if (M <= TC_MAX_ROWS and w_bit == 4 and x.dtype == torch.float16 and K % 64 == 0 and N % 8 == 0 and gs % 32 == 0
+                and gs > 0 and gs & (gs - 1) == 0 and G * (512 if not asym else 320) <= 160 * 1024 and _gidx_is_trivial(g_idx, K, G)):
+            x = x.contiguous()
+            if x.data_ptr() % 16 == 0:
+                y = torch.empty((M, N), dtype=x.dtype, device=x.device)
+                with _on_device(x.device):
+                    rc = _cabi.lib().b200bit_mpq_forward_tc(x.data_ptr(), qweight.contiguous().data_ptr(),
+                                                            scales.contiguous().data_ptr(), zeros.contiguous().data_ptr(),
+                                                            y.data_ptr(), M, K, N, G, w_bit, int(bool(asym)), _cabi.F16,
+                                                            _raw_stream(x.device))
+                if rc:
+                    _cabi.check(rc)
+                return y
         return torch.matmul(x, mpq_dequant(qweight, scales, zeros, g_idx, w_bit, asym))
     x = x.contiguous()
     qweight = qweight.contiguous()

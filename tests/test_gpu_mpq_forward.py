@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 CASES = load_nbit_cases()
 
 
-PATHS = {"auto": (0, 0), "gemv": (1, 0), "mma": (2, 1), "stream": (4, 1), "umma": (5, 1), "pipe": (6, 0), "imma": (7, 0)}
+PATHS = {"auto": (0, 0), "gemv": (1, 0), "mma": (2, 1), "stream": (4, 1), "tc": (5, 1), "pipe": (6, 0), "imma": (7, 0)}
 
 
 def _run(inp, w_bit, asym, path="auto"):
@@ -59,7 +59,7 @@ LLAMA = [(4096, 4096), (4096, 11008), (11008, 4096)]
 
 @pytest.mark.parametrize("K,N", LLAMA)
 @pytest.mark.parametrize("M", [1, 2, 4, 8, 32])
-@pytest.mark.parametrize("path", ["auto", "gemv", "mma", "stream", "umma", "pipe", "imma"])
+@pytest.mark.parametrize("path", ["auto", "gemv", "mma", "stream", "pipe", "imma"])
 def test_llama7b_shapes_4bit_g128(K, N, M, path):
     inp = make_mpq_inputs(K, N, 4, 128, "f16", False, M=M, seed=K + N + M, device="cuda")
     y = _run(inp, 4, False, path)
@@ -71,7 +71,7 @@ def test_llama7b_shapes_4bit_g128(K, N, M, path):
                                          (1, 32), (4, 1024)])
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
 @pytest.mark.parametrize("asym", [False, True])
-@pytest.mark.parametrize("path", ["auto", "gemv", "mma", "stream", "umma", "pipe", "imma"])
+@pytest.mark.parametrize("path", ["auto", "gemv", "mma", "stream", "pipe", "imma"])
 def test_bits_groups_dtypes(w_bit, group, dt, asym, path):
     K, N, M = 2048, 1024, 1
     inp = make_mpq_inputs(K, N, w_bit, group, dt, asym, M=M, seed=w_bit * 1000 + group, device="cuda")
@@ -80,8 +80,8 @@ def test_bits_groups_dtypes(w_bit, group, dt, asym, path):
     assert_close_to_oracles(to_np_f32(y), y_ref, y_exact, dt, f"b{w_bit} g{group} {dt} asym={asym}")
 
 
-@pytest.mark.parametrize("M", [1, 3, 5, 8, 9, 17, 31, 33, 70])
-@pytest.mark.parametrize("path", ["gemv", "mma", "stream", "umma"])
+@pytest.mark.parametrize("M", [1, 3, 5, 8, 9, 17, 31, 33, 70, 129, 300])
+@pytest.mark.parametrize("path", ["auto", "gemv", "mma", "stream", "tc"])
 def test_row_counts(M, path):
     inp = make_mpq_inputs(1024, 512, 4, 128, "f16", False, M=M, seed=M, device="cuda")
     y = _run(inp, 4, False, path)
