@@ -80,6 +80,9 @@ def _input_ready(x, stream):
 
 
 MPQ_FUSED_MAX_ROWS = 32
+# 2-bit: the small-batch kernel needs 85 - 205 us at 32 rows on the Llama-7B shapes, dequantise + dense GEMM 30 - 46 us
+# (profiles/configs_r02.json)
+MPQ_FUSED_MAX_ROWS_2BIT = 8
 TC_MAX_ROWS = 1 << 30      # measured on B200 (profiles/r2_21_tc_kernel_vs_dequant_cublas.jsonl): ahead of dequantise + cuBLAS at every M
 GRAD_INPUT_FUSED_MAX_ROWS = 4
 
@@ -112,7 +115,7 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         if not _gidx_is_trivial(g_idx, K, G):
             raise NotImplementedError("DecodeChain: act-order g_idx is not supported inside a chain")
         return rec.add(x, qweight, scales, zeros, w_bit, asym)
-    if M > MPQ_FUSED_MAX_ROWS and x.dtype != torch.float32:
+    if M > (MPQ_FUSED_MAX_ROWS if w_bit != 2 else MPQ_FUSED_MAX_ROWS_2BIT) and x.dtype != torch.float32:
         # large batches (prefill, training).  Up to TC_MAX_ROWS rows: the tcgen05 kernel (csrc/mpq_tc.cu) -- weights
         # dequantised straight into tensor memory, one pass over the packed matrix, no fp16 copy of W in HBM.  Beyond that
         # (or for shapes it does not cover): dequantise ONCE (one kernel, bit-identical to unpack_qweight) + dense GEMM, the

@@ -86,6 +86,17 @@ def test_row_counts(M, path):
     inp = make_mpq_inputs(1024, 512, 4, 128, "f16", False, M=M, seed=M, device="cuda")
     y = _run(inp, 4, False, path)
     y_ref, y_exact = _oracles(inp, 4, False, "f16", None)
+    if M > 32:
+        # more than 32 rows (whatever path is forced for the small-batch kernels): the tcgen05 kernel multiplies by the
+        # fp16-ROUNDED weight, exactly as the reference's large-batch
+        # path (unpack_qweight + matmul, mpq_layer.py:59-63) -- so the reference-faithful oracle is the yardstick, not the
+        # exact model: 1e-3 normwise, element-wise 2e-3 |y| + 2e-3 rms
+        from helpers import rel_fro, NORMWISE_TOL
+        yn = to_np_f32(y).astype(np.float64)
+        assert rel_fro(yn, y_ref) <= NORMWISE_TOL["f16"]
+        rms = float(np.sqrt(np.mean(np.asarray(y_ref, dtype=np.float64) ** 2)))
+        assert np.all(np.abs(yn - y_ref) <= 2e-3 * np.abs(y_ref) + 2e-3 * rms)
+        return
     assert_close_to_oracles(to_np_f32(y), y_ref, y_exact, "f16", f"M={M}")
 
 
