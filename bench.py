@@ -153,6 +153,13 @@ def cpu_step(inputs):
 
 def run_cpu_arm(steps, warmup):
     import torch
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the reference arm runs on rank 0 alone and takes the whole host
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail:
+        torch.set_num_threads(avail)
     cores = torch.get_num_threads()
     inputs = cpu_layer_inputs()
     for _ in range(warmup):
@@ -434,11 +441,14 @@ def main():
         peak, peak_src = hbm_peak()
         per_launch_us = ms_step * 1e3 / n_launch
         achieved = tok_bytes / (ms_step / 1e3) / 1e9
-        traffic = None
+        # DRAM traffic per launch of the dominant kernel: NOT measured in this run (ncu replays kernels) -- the figure of the
+        # committed `ncu --set full` capture of the same kernel on the same workload, labelled as such
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic_latest.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                ent = json.load(open(tp))["chain" if use_chain else "per_layer"]
+                traffic, traffic_src = ent.get("dram_bytes_per_launch"), "static: " + ent.get("source", "")
             except Exception:
                 traffic = None
         if use_chain:
@@ -465,7 +475,7 @@ def main():
                 "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": x_host.numel() * 2,
                         "d2h_bytes_per_step": y_host.numel() * 2},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "kernel": kernel, "avg_launch_us": per_launch_us,
                              "algorithmic_bytes_per_launch": tok_bytes / n_launch},
                 "clocks": clocks}
