@@ -64,6 +64,7 @@ struct ChainParams {
     int S;                       // ring slots
     int rpg_shift;               // log2(packed rows per group) -- one group size per chain
     int sz_bytes, s_tile_bytes, z_tile_bytes;
+    int poll_depth;              // dependency polls in flight per CTA (1, 2 or 4)
     unsigned long long* trace;   // [grid][CH_TRACE_NODES][8] globaltimer stamps (diagnostics build only)
 };
 
@@ -103,17 +104,29 @@ __device__ __forceinline__ unsigned ch_ld_relaxed(const unsigned* p) {
 // PIPELINED: four relaxed loads in flight -- the counter's final value is seen one round trip after it lands instead of
 // 1.5 on average.  `ordered`: the counter orders plain memory (acquire fence at the end); otherwise it
 // is only a hint and the data validates itself.
-__device__ __forceinline__ void ch_spin(const unsigned* ctr, unsigned want, unsigned* err, bool ordered) {
+__device__ __forceinline__ void ch_spin(const unsigned* ctr, unsigned want, unsigned* err, bool ordered, int depth) {
     unsigned a = ch_ld_relaxed(ctr);
     if (a < want) {
-        unsigned b = ch_ld_relaxed(ctr);
-        unsigned c = ch_ld_relaxed(ctr);
-        unsigned d = ch_ld_relaxed(ctr);
         unsigned spins = 0;
-        while (a < want) {          // `a` is the oldest load in flight; three younger ones are behind it
-            a = b; b = c; c = d;
-            d = ch_ld_relaxed(ctr);
-            if (++spins > CH_SPIN_LIMIT) { atomicExch(err, 1u); break; }
+        if (depth <= 1) {
+            while ((a = ch_ld_relaxed(ctr)) < want)
+                if (++spins > CH_SPIN_LIMIT) { atomicExch(err, 1u); break; }
+        } else if (depth == 2) {
+            unsigned b = ch_ld_relaxed(ctr);
+            while (a < want) {
+                a = b;
+                b = ch_ld_relaxed(ctr);
+                if (++spins > CH_SPIN_LIMIT) { atomicExch(err, 1u); break; }
+            }
+        } else {
+            unsigned b = ch_ld_relaxed(ctr);
+            unsigned c = ch_ld_relaxed(ctr);
+            unsigned d = ch_ld_relaxed(ctr);
+            while (a < want) {          // `a` is the oldest load in flight; three younger ones are behind it
+                a = b; b = c; c = d;
+                d = ch_ld_relaxed(ctr);
+                if (++spins > CH_SPIN_LIMIT) { atomicExch(err, 1u); break; }
+            }
         }
     }
     if (ordered) asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -234,7 +247,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
                                              // finish in order, so a wait covers every earlier node (siblings skip)
                 waited = nd.wx_node;
                 if (lane == 0) {
-                    ch_spin(p.counters + nd.wx_node, unsigned(nodes_s[nd.wx_node].strips), err_flag, nd.xll == nullptr);
+                    ch_spin(p.counters + nd.wx_node, unsigned(nodes_s[nd.wx_node].strips), err_flag, nd.xll == nullptr, p.poll_depth);
                     mbar_arrive(ready);
                     if constexpr (TRACE) { if (p.trace && node < CH_TRACE_NODES) p.trace[(size_t(bid) * CH_TRACE_NODES + node) * 8 + 4] = st_gtime(); }
                 }
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
                 if (par) ++use1; else ++use0;
                 par ^= 1;
                 if (nd.wy_node >= 0) {       // write-after-read / write-after-write: the buffer behind y was used by node wy_node
-                    if (lane == 0) ch_spin(p.counters + nd.wy_node, unsigned(nodes_s[nd.wy_node].strips), err_flag, true);
+                    if (lane == 0) ch_spin(p.counters + nd.wy_node, unsigned(nodes_s[nd.wy_node].strips), err_flag, true, p.poll_depth);
                     __syncwarp();
                 }
                 const int width = strip < nd.n28 ? IM_COLS : 24;

@@ -41,6 +41,9 @@ struct TcParams {
     uint16_t* y;              // [M, N] f16
     int M, K, N, G;
     int gs, gs_shift;         // group size (k) = 1 << gs_shift
+    int splits;               // split-K factor (grid.z): > 1 when the tiles alone would leave most SMs idle (small M)
+    float* part;              // [splits][M][N] fp32 partial results (splits > 1)
+    unsigned* tickets;        // [tiles] zero-initialised, self-resetting (splits > 1)
     int asym;
 };
 
@@ -118,7 +121,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
-    const int stages = p.K / TC_KS;
+    // this CTA's share of the k-stages (split-K over grid.z)
+    const int stages_all = p.K / TC_KS;
+    const int s_beg = int((long long)stages_all * blockIdx.z / p.splits), s_end = int((long long)stages_all * (blockIdx.z + 1) / p.splits);
+    const int stages = s_end - s_beg;
 
     if (tid == 0) {
         for (int i = 0; i < TC_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
             // one box = 64 k (128 bytes) x 128 tokens, 128-byte swizzled: rows of 128 B, 8-row atoms of 1 KB.  (Boxes of 8 k
             // = 16-byte rows in the no-swizzle layout cost 1024 sixteen-byte requests per stage: 1800 clk per stage
             // measured, 7x the tensor time.)
-            um_tma_2d(xst + slot * TC_X_STAGE_BYTES, &tm_x, s * TC_KS, m0, &x_full[slot], leader);
+            um_tma_2d(xst + slot * TC_X_STAGE_BYTES, &tm_x, (s_beg + s) * TC_KS, m0, &x_full[slot], leader);
         }
     } else if (warp == TC_DQ_WARPS + 1) {
         // ===================== MMA issuer =====================
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
         uint32_t wr[TC_PF][8];
         auto load_words = [&](int s, uint32_t (&w)[8]) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = (col_ok && s < stages) ? ldg_nc_u32(wp + size_t(s * 8 + i) * p.N) : 0u;
+            for (int i = 0; i < 8; ++i) w[i] = (col_ok && s < stages) ? ldg_nc_u32(wp + size_t((s_beg + s) * 8 + i) * p.N) : 0u;
         };
 #pragma unroll
         for (int u = 0; u < TC_PF; ++u) load_words(grp + 4 * u, wr[u]);
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
                     uint32_t regs[32];
                     // group parameters once per stage, not per word: a 64-k stage lies in one group (groups >= 64) or in
                     // two (32-k groups); groups are 32 * 2^i wide
-                    const int gA = (s * TC_KS) >> p.gs_shift, gB = (s * TC_KS + 32) >> p.gs_shift;
+                    const int gA = ((s_beg + s) * TC_KS) >> p.gs_shift, gB = ((s_beg + s) * TC_KS + 32) >> p.gs_shift;
                     if (gA != g_prev) {
                         g_prev = gA;
                         group_params(gA, s512, mz);
@@ -258,10 +264,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
             tc_ld32(tm_d + (uint32_t(q4 * 32) << 16) + t0, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (col_ok) {
+                if (p.splits == 1) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int m = m0 + t0 + j;
-                    if (m < p.M) p.y[size_t(m) * p.N + n] = __half_as_ushort(__float2half_rn(v[j]));
+                    for (int j = 0; j < 32; ++j) {
+                        const int m = m0 + t0 + j;
+                        if (m < p.M) p.y[size_t(m) * p.N + n] = __half_as_ushort(__float2half_rn(v[j]));
+                    }
+                } else {
+                    float* dst = p.part + size_t(blockIdx.z) * p.M * p.N;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int m = m0 + t0 + j;
+                        if (m < p.M) __stcg(dst + size_t(m) * p.N + n, v[j]);
+                    }
+                }
+            }
+        }
+        if (p.splits > 1) {
+            // split-K: the CTA that draws the last ticket of the tile sums the partial tiles in split order (deterministic)
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_DQ_WARPS * 32) : "memory");
+            unsigned* flag = reinterpret_cast<unsigned*>(tmem_slot) + 1;
+            const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+            if (tid == 0) *flag = atomicAdd(p.tickets + tile, 1u);
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_DQ_WARPS * 32) : "memory");
+            if (*flag == unsigned(p.splits) - 1u) {
+                __threadfence();
+                if (tid == 0) p.tickets[tile] = 0u;
+                const int cols = min(TC_BN, p.N - n0), rows = min(TC_BM, p.M - m0);
+                for (int i = tid; i < rows * (TC_BN / 2); i += TC_DQ_WARPS * 32) {
+                    const int r = i / (TC_BN / 2), c2 = (i % (TC_BN / 2)) * 2;
+                    if (c2 < cols) {
+                        const size_t off = size_t(m0 + r) * p.N + n0 + c2;
+                        float2 acc = make_float2(0.f, 0.f);
+                        for (int z = 0; z < p.splits; ++z) {
+                            const float2 t = __ldcg(reinterpret_cast<const float2*>(p.part + size_t(z) * p.M * p.N + off));
+                            acc.x += t.x; acc.y += t.y;
+                        }
+                        *reinterpret_cast<__half2*>(p.y + off) = __floats2half2_rn(acc.x, acc.y);
+                    }
                 }
             }
         }
@@ -278,7 +319,8 @@ using namespace b200bit;
 
 // y[M,N] = x[M,K] @ dequant(qweight): 4-bit, f16, contiguous groups of 32*i values, K % 64 == 0, N % 8 == 0.
 extern "C" int b200bit_mpq_forward_tc(const void* x, const int32_t* qweight, const void* scales, const void* zeros, void* y,
-                                      int M, int K, int N, int G, int w_bit, int asym, int dtype, void* stream_) {
+                                      int M, int K, int N, int G, int w_bit, int asym, int dtype, void* workspace,
+                                      size_t workspace_bytes, void* stream_) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
     B200_REQUIRE(x && qweight && scales && zeros && y, B200BIT_ERR_ARG, "mpq_forward_tc: null pointer argument");
     B200_REQUIRE(w_bit == 4 && dtype == B200BIT_F16, B200BIT_ERR_UNSUPPORTED, "mpq_forward_tc: w_bit=%d dtype code %d (4-bit, f16)", w_bit, dtype);
@@ -311,7 +353,20 @@ extern "C" int b200bit_mpq_forward_tc(const void* x, const int32_t* qweight, con
         B200_CUDA_OK(cudaFuncSetAttribute(mpq_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured_dev[dev & 63] = true;
     }
-    dim3 grid((N + TC_BN - 1) / TC_BN, (M + BM - 1) / BM);
+    // split-K when the tiles alone leave most SMs idle (M <= 128 on a 4096-column layer is 32 tiles): partial tiles in the
+    // caller's workspace, the CTA that draws the last ticket of a tile adds them up in split order
+    const int tiles = ((N + TC_BN - 1) / TC_BN) * ((M + BM - 1) / BM);
+    const int stages = K / TC_KS;
+    int splits = 1;
+    while (splits < 8 && tiles * splits * 2 <= sm_count() && stages / (splits * 2) >= 8) splits *= 2;
+    if (splits > 1) {
+        const size_t need = size_t(B200BIT_WS_TICKET_BYTES) + size_t(splits) * M * N * sizeof(float);
+        if (!workspace || workspace_bytes < need || size_t(tiles) * sizeof(unsigned) > B200BIT_WS_ZERO_OFFSET) splits = 1;
+    }
+    p.splits = splits;
+    p.tickets = reinterpret_cast<unsigned*>(workspace);
+    p.part = splits > 1 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B200BIT_WS_TICKET_BYTES) : nullptr;
+    dim3 grid((N + TC_BN - 1) / TC_BN, (M + BM - 1) / BM, splits);
     if (BM == 256) mpq_tc_kernel<256><<<grid, TC_THREADS, smem, st>>>(tm_x, p);
     else mpq_tc_kernel<128><<<grid, TC_THREADS, smem, st>>>(tm_x, p);
     B200_CUDA_OK(cudaGetLastError());

@@ -83,7 +83,7 @@ MPQ_FUSED_MAX_ROWS = 32
 # 2-bit: the small-batch kernel needs 85 - 205 us at 32 rows on the Llama-7B shapes, dequantise + dense GEMM 30 - 46 us
 # (profiles/configs_r02.json)
 MPQ_FUSED_MAX_ROWS_2BIT = 8
-TC_MAX_ROWS = 1 << 30      # measured on B200 (profiles/r2_21_tc_kernel_vs_dequant_cublas.jsonl): ahead of dequantise + cuBLAS at every M
+TC_MIN_ROWS = 16           # from 17 rows on the tcgen05 kernel takes every shape it covers
 GRAD_INPUT_FUSED_MAX_ROWS = 4
 
 
@@ -115,26 +115,33 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         if not _gidx_is_trivial(g_idx, K, G):
             raise NotImplementedError("DecodeChain: act-order g_idx is not supported inside a chain")
         return rec.add(x, qweight, scales, zeros, w_bit, asym)
-    if M > (MPQ_FUSED_MAX_ROWS if w_bit != 2 else MPQ_FUSED_MAX_ROWS_2BIT) and x.dtype != torch.float32:
-        # large batches (prefill, training).  Up to TC_MAX_ROWS rows: the tcgen05 kernel (csrc/mpq_tc.cu) -- weights
-        # dequantised straight into tensor memory, one pass over the packed matrix, no fp16 copy of W in HBM.  Beyond that
-        # (or for shapes it does not cover): dequantise ONCE (one kernel, bit-identical to unpack_qweight) + dense GEMM, the
-        # switch the reference makes at 32 rows (mpq_layer.py:59-63).
+    if M > TC_MIN_ROWS and x.dtype != torch.float32:
+        # batches (bs = 32 serving, prefill, training).  The tcgen05 kernel (csrc/mpq_tc.cu) -- weights dequantised straight
+        # into tensor memory, one pass over the packed matrix for any M, split-K for small M, no fp16 copy of W in HBM --
+        # takes every shape it covers from 17 rows on (measured against the mma.sync small-batch kernel at 32 rows:
+        # 26.7 vs 39.1 us on 4096x11008, 26.2 vs 35.4 us on 11008x4096, 20.9 vs 18.8 us on 4096x4096; against dequantise +
+        # cuBLAS it is ahead at every M, profiles/r2_25_tc_kernel_split_k.jsonl).  Shapes it does not cover: the
+        # small-batch kernels up to 32 rows (2-bit: 8), then dequantise ONCE (one kernel, bit-identical to unpack_qweight) +
+        # dense GEMM -- the switch the reference makes at 32 rows (mpq_layer.py:59-63).
         gs = K // G if G and K % G == 0 else 0
-        if (M <= TC_MAX_ROWS and w_bit == 4 and x.dtype == torch.float16 and K % 64 == 0 and N % 8 == 0 and gs % 32 == 0
-                and gs > 0 and gs & (gs - 1) == 0 and G * (512 if not asym else 320) <= 160 * 1024 and _gidx_is_trivial(g_idx, K, G)):
+        tc_ok = (w_bit == 4 and x.dtype == torch.float16 and K % 64 == 0 and N % 8 == 0 and gs % 32 == 0 and gs > 0
+                 and gs & (gs - 1) == 0 and G * (512 if not asym else 320) <= 160 * 1024 and _gidx_is_trivial(g_idx, K, G))
+        if tc_ok:
             x = x.contiguous()
             if x.data_ptr() % 16 == 0:
                 y = torch.empty((M, N), dtype=x.dtype, device=x.device)
                 with _on_device(x.device):
+                    stream = _raw_stream(x.device)
+                    ws = _cabi.workspace(x.device, stream, _cabi.WS_TICKET_BYTES + 8 * min(M, 256) * N * 4 if M <= 256 else 0)
                     rc = _cabi.lib().b200bit_mpq_forward_tc(x.data_ptr(), qweight.contiguous().data_ptr(),
                                                             scales.contiguous().data_ptr(), zeros.contiguous().data_ptr(),
                                                             y.data_ptr(), M, K, N, G, w_bit, int(bool(asym)), _cabi.F16,
-                                                            _raw_stream(x.device))
+                                                            ws.data_ptr(), ws.numel(), stream)
                 if rc:
                     _cabi.check(rc)
                 return y
-        return torch.matmul(x, mpq_dequant(qweight, scales, zeros, g_idx, w_bit, asym))
+        if M > (MPQ_FUSED_MAX_ROWS if w_bit != 2 else MPQ_FUSED_MAX_ROWS_2BIT):
+            return torch.matmul(x, mpq_dequant(qweight, scales, zeros, g_idx, w_bit, asym))
     x = x.contiguous()
     qweight = qweight.contiguous()
     scales = scales.contiguous()

@@ -58,13 +58,27 @@ LLAMA = [(4096, 4096), (4096, 11008), (11008, 4096)]
 
 
 @pytest.mark.parametrize("K,N", LLAMA)
-@pytest.mark.parametrize("M", [1, 2, 4, 8, 32])
+@pytest.mark.parametrize("M", [1, 2, 4, 8, 16])
 @pytest.mark.parametrize("path", ["auto", "gemv", "mma", "stream", "pipe", "imma"])
 def test_llama7b_shapes_4bit_g128(K, N, M, path):
     inp = make_mpq_inputs(K, N, 4, 128, "f16", False, M=M, seed=K + N + M, device="cuda")
     y = _run(inp, 4, False, path)
     y_ref, y_exact = _oracles(inp, 4, False, "f16", None)
     assert_close_to_oracles(to_np_f32(y), y_ref, y_exact, "f16", f"{K}x{N} M={M}")
+
+
+@pytest.mark.parametrize("w_bit,group", [(8, 128), (2, 32)])
+@pytest.mark.parametrize("M", [8, 17, 32])
+@pytest.mark.parametrize("path", ["auto", "mma", "stream"])
+def test_small_batch_kernels_beyond_16_rows(w_bit, group, M, path):
+    """4-bit f16 batches above 16 rows belong to the tcgen05 kernel; the mma.sync small-batch kernels keep the
+    configurations it does not cover (8-bit up to 32 rows, 2-bit up to 8): exact-model tolerance, as for M = 1"""
+    if w_bit == 2 and M > 8:
+        pytest.skip("2-bit above 8 rows: dequantise + dense GEMM (tests/test_gpu_configs.py)")
+    inp = make_mpq_inputs(2048, 1024, w_bit, group, "f16", False, M=M, seed=w_bit * 100 + M, device="cuda")
+    y = _run(inp, w_bit, False, path)
+    y_ref, y_exact = _oracles(inp, w_bit, False, "f16", None)
+    assert_close_to_oracles(to_np_f32(y), y_ref, y_exact, "f16", f"b{w_bit} M={M} {path}")
 
 
 @pytest.mark.parametrize("w_bit,group", [(4, 128), (4, 32), (4, 64), (2, 32), (2, 128), (2, 16), (8, 128), (1, 128),
@@ -86,8 +100,8 @@ def test_row_counts(M, path):
     inp = make_mpq_inputs(1024, 512, 4, 128, "f16", False, M=M, seed=M, device="cuda")
     y = _run(inp, 4, False, path)
     y_ref, y_exact = _oracles(inp, 4, False, "f16", None)
-    if M > 32:
-        # more than 32 rows (whatever path is forced for the small-batch kernels): the tcgen05 kernel multiplies by the
+    if M > 16:
+        # more than 16 rows (whatever path is forced for the small-batch kernels): the tcgen05 kernel multiplies by the
         # fp16-ROUNDED weight, exactly as the reference's large-batch
         # path (unpack_qweight + matmul, mpq_layer.py:59-63) -- so the reference-faithful oracle is the yardstick, not the
         # exact model: 1e-3 normwise, element-wise 2e-3 |y| + 2e-3 rms

@@ -10,6 +10,7 @@ from bitorch_engine_b200.extensions import q_linear_cuda
 from helpers import make_mpq_inputs
 
 lib = _cabi.lib()
+WS = torch.zeros(512 << 20, dtype=torch.uint8, device="cuda")
 quick = len(sys.argv) > 1
 
 
@@ -19,7 +20,7 @@ def tc(x, inp, asym):
     y = torch.empty((M, N), dtype=torch.float16, device=x.device)
     _cabi.check(lib.b200bit_mpq_forward_tc(x.data_ptr(), inp["qweight"].data_ptr(), inp["scales"].data_ptr(), inp["zeros"].data_ptr(),
                                            y.data_ptr(), M, K, N, inp["scales"].shape[0], 4, int(asym), _cabi.F16,
-                                           torch.cuda.current_stream().cuda_stream))
+                                           WS.data_ptr(), WS.numel(), torch.cuda.current_stream().cuda_stream))
     return y
 
 
@@ -37,7 +38,7 @@ shapes = [(4096, 4096), (4096, 11008), (11008, 4096)] + ([] if quick else [(4096
 for K, N in shapes:
     for group, asym in ((128, False), (128, True), (32, False)):
         if quick and (asym or group != 128): continue
-        for M in (33, 64, 128, 512, 2048):
+        for M in (16, 32, 33, 64, 128, 512, 2048):
             inp = make_mpq_inputs(K, N, 4, group, "f16", asym, M=M, seed=K + N + M, device="cuda")
             x = inp["x"]
             W = q_linear_cuda.mpq_dequant(inp["qweight"], inp["scales"], inp["zeros"], inp["g_idx"], 4, asym, fused=True)
@@ -56,5 +57,7 @@ for K, N in shapes:
                 row["dequant_cublas_us"] = round(t_us(lambda: torch.matmul(x, q_linear_cuda.mpq_dequant(inp["qweight"], inp["scales"], inp["zeros"], inp["g_idx"], 4, asym))), 2)
                 row["cublas_only_us"] = round(t_us(lambda: torch.matmul(x, W)), 2)
                 row["tc_TFLOPs"] = round(2 * M * K * N / row["tc_us"] / 1e6, 1)
+                if M <= 32:
+                    row["small_batch_kernel_us"] = round(t_us(lambda: q_linear_cuda.mpq_forward(x, inp["qweight"], inp["scales"], inp["zeros"], inp["g_idx"], 16, 4, asym)), 2)
             print(json.dumps(row), flush=True)
             assert err < 2e-3, "tc kernel parity"

@@ -11,6 +11,6 @@ inp = make_mpq_inputs(K, N, 4, 128, "f16", False, M=M, seed=1, device="cuda")
 y = torch.empty((M, N), dtype=torch.float16, device="cuda")
 for _ in range(3):
     _cabi.check(lib.b200bit_mpq_forward_tc(inp["x"].data_ptr(), inp["qweight"].data_ptr(), inp["scales"].data_ptr(), inp["zeros"].data_ptr(),
-                                           y.data_ptr(), M, K, N, K // 128, 4, 0, _cabi.F16, torch.cuda.current_stream().cuda_stream))
+                                           y.data_ptr(), M, K, N, K // 128, 4, 0, _cabi.F16, None, 0, torch.cuda.current_stream().cuda_stream))
 torch.cuda.synchronize()
 print("ok")
