@@ -781,7 +781,7 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
     }
     chain_invalidate(stream);      // every other kernel triggers its dependents before its own dependency wait
     // ---- more than 16 rows: tcgen05 batched kernel (mpq_tc.cu), one pass over the packed matrix ----
-    if (M > (g_path == 5 ? 0 : 16) && (g_path == 0 || g_path == 5) && trivial && w_bit == 4 && dtype == B200BIT_F16 && K % 64 == 0 && N % 8 == 0 &&
+    if (M > (g_path == 5 ? 0 : (w_bit == 2 ? 8 : 16)) && (g_path == 0 || g_path == 5) && trivial && (w_bit == 4 || w_bit == 2) && dtype == B200BIT_F16 && K % 64 == 0 && N % 8 == 0 &&
         K % G == 0 && (K / G) % 32 == 0 && ((K / G) & (K / G - 1)) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
         size_t(G) * (asym ? 320 : 512) <= size_t(160) * 1024)
         return b200bit_mpq_forward_tc(x, qweight, scales, zeros, y, M, K, N, G, w_bit, asym, dtype, workspace, workspace_bytes, stream_);

@@ -35,9 +35,9 @@ constexpr int TC_THREADS = (TC_DQ_WARPS + 2) * 32;
 constexpr int TC_TMEM_COLS = 512;      // D: BM columns (fp32 x BM tokens: 128 or 256) | A: 8 stages x 32 columns
 
 struct TcParams {
-    const uint32_t* qw;       // [K/8, N]
+    const uint32_t* qw;       // [K * bits / 32, N]
     const uint16_t* scales;   // [G, N] f16
-    const void* zeros;        // sym: f16 [G, N]; asym: packed int32 [G, N/8]
+    const void* zeros;        // sym: f16 [G, N]; asym: packed int32 [G, N * bits / 32]
     uint16_t* y;              // [M, N] f16
     int M, K, N, G;
     int gs, gs_shift;         // group size (k) = 1 << gs_shift
@@ -102,9 +102,26 @@ __device__ __forceinline__ void tc_dequant4(uint32_t w, uint32_t s512, uint32_t 
     for (int c = 0; c < 4; ++c) asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(out[c]) : "r"(h[c]), "r"(s512), "r"(mz));
 }
 
+// sixteen two-bit codes (LSB first) -> eight half2 registers (k0,k1) ... (k14,k15); same fp8 reinterpretation (0..3 are e4m3
+// subnormals)
+__device__ __forceinline__ void tc_dequant2(uint32_t w, uint32_t s512, uint32_t mz, uint32_t* out) {
+    const uint32_t t0 = w & 0x03030303u, t1 = (w >> 2) & 0x03030303u, t2 = (w >> 4) & 0x03030303u, t3 = (w >> 6) & 0x03030303u;
+    const uint32_t a = __byte_perm(t0, t1, 0x5140), b = __byte_perm(t0, t1, 0x7362);     // (q0,q1,q4,q5), (q8,q9,q12,q13)
+    const uint32_t c = __byte_perm(t2, t3, 0x5140), d = __byte_perm(t2, t3, 0x7362);     // (q2,q3,q6,q7), (q10,q11,q14,q15)
+    uint32_t h[8];
+    tc_cvt_e4m3x4(a, h[0], h[2]);
+    tc_cvt_e4m3x4(c, h[1], h[3]);
+    tc_cvt_e4m3x4(b, h[4], h[6]);
+    tc_cvt_e4m3x4(d, h[5], h[7]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(out[i]) : "r"(h[i]), "r"(s512), "r"(mz));
+}
+
 // TC_BM = tokens per CTA (UMMA N): 128, or 256 for large batches (a dequantised weight then feeds twice the MMA work)
-template <int TC_BM>
+template <int TC_BM, int BITS>
 __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const TcParams p) {
+    constexpr int WPS = 2 * BITS;                           // packed words of one column per 64-k stage
+    constexpr int NB = 32 / BITS;                           // codes per word
     constexpr int TC_X_STAGE_BYTES = TC_BM * TC_KS * 2;     // 16 / 32 KB
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     unsigned char* xst = tc_smem;                                             // x ring: 4 x 16 KB
@@ -143,10 +160,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
         if (!p.asym) reinterpret_cast<uint16_t*>(z_sm)[i] = col < p.N ? reinterpret_cast<const uint16_t*>(p.zeros)[size_t(g) * p.N + col] : uint16_t(0);
     }
     if (p.asym)
-        for (int i = tid; i < p.G * (TC_BN / 8); i += TC_THREADS) {
-            const int g = i / (TC_BN / 8), c = i % (TC_BN / 8);
-            const int wcol = n0 / 8 + c;
-            reinterpret_cast<uint32_t*>(z_sm)[i] = wcol < p.N / 8 ? reinterpret_cast<const uint32_t*>(p.zeros)[size_t(g) * (p.N / 8) + wcol] : 0u;
+        for (int i = tid; i < p.G * (TC_BN / NB); i += TC_THREADS) {
+            const int g = i / (TC_BN / NB), c = i % (TC_BN / NB);
+            const int wcol = n0 / NB + c;
+            reinterpret_cast<uint32_t*>(z_sm)[i] = wcol < p.N / NB ? reinterpret_cast<const uint32_t*>(p.zeros)[size_t(g) * (p.N / NB) + wcol] : 0u;
         }
     tc_fence_before();
     __syncthreads();
@@ -199,10 +216,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
         // packed words of the group's next two stages (8 global stages ahead) wait in registers: a stage is ~0.13 us of
         // tensor time, a global load ~1 us away
         constexpr int TC_PF = 2;
-        uint32_t wr[TC_PF][8];
-        auto load_words = [&](int s, uint32_t (&w)[8]) {
+        uint32_t wr[TC_PF][WPS];
+        auto load_words = [&](int s, uint32_t (&w)[WPS]) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = (col_ok && s < stages) ? ldg_nc_u32(wp + size_t((s_beg + s) * 8 + i) * p.N) : 0u;
+            for (int i = 0; i < WPS; ++i) w[i] = (col_ok && s < stages) ? ldg_nc_u32(wp + size_t((s_beg + s) * WPS + i) * p.N) : 0u;
         };
 #pragma unroll
         for (int u = 0; u < TC_PF; ++u) load_words(grp + 4 * u, wr[u]);
@@ -213,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
         auto group_params = [&](int g, uint32_t& s2, uint32_t& z2) {
             const float sf = __half2float(__ushort_as_half(s_sm[g * TC_BN + cl]));
             float zf;
-            if (p.asym) zf = sf * float(((reinterpret_cast<const uint32_t*>(z_sm)[g * (TC_BN / 8) + (cl >> 3)] >> ((cl & 7) * 4)) & 15u) + 1u);
+            if (p.asym) zf = sf * float(((reinterpret_cast<const uint32_t*>(z_sm)[g * (TC_BN / NB) + cl / NB] >> ((cl % NB) * BITS)) & ((1u << BITS) - 1u)) + 1u);
             else zf = __half2float(__ushort_as_half(reinterpret_cast<const uint16_t*>(z_sm)[g * TC_BN + cl]));
             const uint32_t sh = __half_as_ushort(__float2half_rn(512.f * sf));
             const uint32_t zh = __half_as_ushort(__float2half_rn(-zf));
@@ -239,8 +256,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
                         g_prev = -1;
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        tc_dequant4(wr[u][i], i < 4 ? s512 : s512b, i < 4 ? mz : mzb, regs + 4 * i);
+                    for (int i = 0; i < WPS; ++i) {
+                        if constexpr (BITS == 4) tc_dequant4(wr[u][i], i < 4 ? s512 : s512b, i < 4 ? mz : mzb, regs + 4 * i);
+                        else tc_dequant2(wr[u][i], i < 2 ? s512 : s512b, i < 2 ? mz : mzb, regs + 8 * i);
+                    }
                     load_words(s + 4 * TC_PF, wr[u]);
                     const int as = s % TC_ASTAGES;                 // grp or grp + 4
                     if (use >= 2) { tc_wait(&a_empty[as], ((use >> 1) - 1) & 1); tc_fence_after(); }
@@ -323,7 +342,8 @@ extern "C" int b200bit_mpq_forward_tc(const void* x, const int32_t* qweight, con
                                       size_t workspace_bytes, void* stream_) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
     B200_REQUIRE(x && qweight && scales && zeros && y, B200BIT_ERR_ARG, "mpq_forward_tc: null pointer argument");
-    B200_REQUIRE(w_bit == 4 && dtype == B200BIT_F16, B200BIT_ERR_UNSUPPORTED, "mpq_forward_tc: w_bit=%d dtype code %d (4-bit, f16)", w_bit, dtype);
+    B200_REQUIRE((w_bit == 4 || w_bit == 2) && dtype == B200BIT_F16, B200BIT_ERR_UNSUPPORTED, "mpq_forward_tc: w_bit=%d dtype code %d (2- / 4-bit, f16)", w_bit, dtype);
+    B200_REQUIRE(!asym || N % (32 / w_bit) == 0, B200BIT_ERR_SHAPE, "mpq_forward_tc: asym needs N %% %d == 0", 32 / w_bit);
     B200_REQUIRE(M > 0 && K > 0 && N > 0 && G > 0 && K % G == 0 && K % TC_KS == 0 && N % 8 == 0 && (K / G) % 32 == 0, B200BIT_ERR_SHAPE,
                  "mpq_forward_tc: bad sizes M=%d K=%d N=%d G=%d (K %% 64 == 0, N %% 8 == 0, groups of 32*i)", M, K, N, G);
     B200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, B200BIT_ERR_ARG, "mpq_forward_tc: x must be 16-byte aligned");
@@ -343,14 +363,16 @@ extern "C" int b200bit_mpq_forward_tc(const void* x, const int32_t* qweight, con
     p.gs_shift = 0;
     while ((1 << p.gs_shift) < p.gs) ++p.gs_shift;
     B200_REQUIRE((1 << p.gs_shift) == p.gs, B200BIT_ERR_UNSUPPORTED, "mpq_forward_tc: group size %d is not a power of two", p.gs);
-    const size_t smem = size_t(TC_XSTAGES) * BM * TC_KS * 2 + 256 + size_t(G) * TC_BN * 2 + (asym ? size_t(G) * (TC_BN / 8) * 4 : size_t(G) * TC_BN * 2);
+    const size_t smem = size_t(TC_XSTAGES) * BM * TC_KS * 2 + 256 + size_t(G) * TC_BN * 2 + (asym ? size_t(G) * (TC_BN / (32 / w_bit)) * 4 : size_t(G) * TC_BN * 2);
     B200_REQUIRE(smem <= 227 * 1024, B200BIT_ERR_UNSUPPORTED, "mpq_forward_tc: %d groups do not fit the shared-memory parameter table", G);
     static bool configured_dev[64] = {false};
     int dev = 0;
     B200_CUDA_OK(cudaGetDevice(&dev));
     if (!configured_dev[dev & 63]) {
-        B200_CUDA_OK(cudaFuncSetAttribute(mpq_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        B200_CUDA_OK(cudaFuncSetAttribute(mpq_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(mpq_tc_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(mpq_tc_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(mpq_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(mpq_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured_dev[dev & 63] = true;
     }
     // split-K when the tiles alone leave most SMs idle (M <= 128 on a 4096-column layer is 32 tiles): partial tiles in the
@@ -367,8 +389,13 @@ extern "C" int b200bit_mpq_forward_tc(const void* x, const int32_t* qweight, con
     p.tickets = reinterpret_cast<unsigned*>(workspace);
     p.part = splits > 1 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B200BIT_WS_TICKET_BYTES) : nullptr;
     dim3 grid((N + TC_BN - 1) / TC_BN, (M + BM - 1) / BM, splits);
-    if (BM == 256) mpq_tc_kernel<256><<<grid, TC_THREADS, smem, st>>>(tm_x, p);
-    else mpq_tc_kernel<128><<<grid, TC_THREADS, smem, st>>>(tm_x, p);
+    if (w_bit == 4) {
+        if (BM == 256) mpq_tc_kernel<256, 4><<<grid, TC_THREADS, smem, st>>>(tm_x, p);
+        else mpq_tc_kernel<128, 4><<<grid, TC_THREADS, smem, st>>>(tm_x, p);
+    } else {
+        if (BM == 256) mpq_tc_kernel<256, 2><<<grid, TC_THREADS, smem, st>>>(tm_x, p);
+        else mpq_tc_kernel<128, 2><<<grid, TC_THREADS, smem, st>>>(tm_x, p);
+    }
     B200_CUDA_OK(cudaGetLastError());
     return B200BIT_OK;
 }

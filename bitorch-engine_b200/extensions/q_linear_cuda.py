@@ -115,7 +115,7 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         if not _gidx_is_trivial(g_idx, K, G):
             raise NotImplementedError("DecodeChain: act-order g_idx is not supported inside a chain")
         return rec.add(x, qweight, scales, zeros, w_bit, asym)
-    if M > TC_MIN_ROWS and x.dtype != torch.float32:
+    if M > (TC_MIN_ROWS if w_bit != 2 else MPQ_FUSED_MAX_ROWS_2BIT) and x.dtype != torch.float32:
         # batches (bs = 32 serving, prefill, training).  The tcgen05 kernel (csrc/mpq_tc.cu) -- weights dequantised straight
         # into tensor memory, one pass over the packed matrix for any M, split-K for small M, no fp16 copy of W in HBM --
         # takes every shape it covers from 17 rows on (measured against the mma.sync small-batch kernel at 32 rows:
@@ -124,7 +124,7 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         # small-batch kernels up to 32 rows (2-bit: 8), then dequantise ONCE (one kernel, bit-identical to unpack_qweight) +
         # dense GEMM -- the switch the reference makes at 32 rows (mpq_layer.py:59-63).
         gs = K // G if G and K % G == 0 else 0
-        tc_ok = (w_bit == 4 and x.dtype == torch.float16 and K % 64 == 0 and N % 8 == 0 and gs % 32 == 0 and gs > 0
+        tc_ok = (w_bit in (2, 4) and x.dtype == torch.float16 and K % 64 == 0 and N % 8 == 0 and gs % 32 == 0 and gs > 0
                  and gs & (gs - 1) == 0 and G * (512 if not asym else 320) <= 160 * 1024 and _gidx_is_trivial(g_idx, K, G))
         if tc_ok:
             x = x.contiguous()

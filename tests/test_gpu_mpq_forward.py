@@ -100,7 +100,7 @@ def test_row_counts(M, path):
     inp = make_mpq_inputs(1024, 512, 4, 128, "f16", False, M=M, seed=M, device="cuda")
     y = _run(inp, 4, False, path)
     y_ref, y_exact = _oracles(inp, 4, False, "f16", None)
-    if M > 16:
+    if M > 16 or path == "tc":
         # more than 16 rows (whatever path is forced for the small-batch kernels): the tcgen05 kernel multiplies by the
         # fp16-ROUNDED weight, exactly as the reference's large-batch
         # path (unpack_qweight + matmul, mpq_layer.py:59-63) -- so the reference-faithful oracle is the yardstick, not the
