@@ -227,6 +227,8 @@ int b200bit_mpq_chain_launch(void* plan_device, const int* info16, unsigned flag
     p.z_tile_bytes = info16[CI_ZTILE];
     static const int poll_depth = getenv("B200BIT_CHAIN_POLLS") ? atoi(getenv("B200BIT_CHAIN_POLLS")) : 1;     // sweep hook; measured 1 / 2 / 4 in flight: 1164.6 / 1162.4 / 1156.5 tokens/s
     p.poll_depth = poll_depth;
+    static const int early_pct = getenv("B200BIT_CHAIN_EARLY") ? atoi(getenv("B200BIT_CHAIN_EARLY")) : 50;     // sweep hook; measured 0 / 25 / 50 / 75 / 95 %: 1153.6 / 1220.0 / 1239.5 / 1234.9 / 1232.2 tokens/s
+    p.early_pct = early_pct < 0 ? 0 : (early_pct > 99 ? 99 : early_pct);
     p.trace = trace_buffer();
     ChainLaunch l{};
     l.F = info16[CI_F]; l.grid = info16[CI_GRID]; l.asym = info16[CI_ASYM] != 0; l.bf16 = info16[CI_BF16] != 0;

@@ -65,6 +65,7 @@ struct ChainParams {
     int rpg_shift;               // log2(packed rows per group) -- one group size per chain
     int sz_bytes, s_tile_bytes, z_tile_bytes;
     int poll_depth;              // dependency polls in flight per CTA (1, 2 or 4)
+    int early_pct;               // shadow readers start pulling x once (100 - early_pct) % of the producer's strips are counted
     unsigned long long* trace;   // [grid][CH_TRACE_NODES][8] globaltimer stamps (diagnostics build only)
 };
 
@@ -247,7 +248,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
                                              // finish in order, so a wait covers every earlier node (siblings skip)
                 waited = nd.wx_node;
                 if (lane == 0) {
-                    ch_spin(p.counters + nd.wx_node, unsigned(nodes_s[nd.wx_node].strips), err_flag, nd.xll == nullptr, p.poll_depth);
+                    // shadow words validate themselves, so their readers may start before the last strip is counted: the
+                    // pull (one loaded L2 round trip) then overlaps the stragglers instead of following them
+                    unsigned want = unsigned(nodes_s[nd.wx_node].strips);
+                    if (nd.xll != nullptr) { want -= want * unsigned(p.early_pct) / 100u; want = want ? want : 1u; }
+                    ch_spin(p.counters + nd.wx_node, want, err_flag, nd.xll == nullptr, p.poll_depth);
                     mbar_arrive(ready);
                     if constexpr (TRACE) { if (p.trace && node < CH_TRACE_NODES) p.trace[(size_t(bid) * CH_TRACE_NODES + node) * 8 + 4] = st_gtime(); }
                 }
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
                 }
                 if (__all_sync(0xffffffffu, have)) break;
                 if (++spins > (CH_SPIN_LIMIT >> 2)) { if (lane == 0) atomicExch(err_flag, 1u); break; }
-                __nanosleep(64);        // rare: the hint counter said the words are on their way
+                if (p.early_pct == 0) __nanosleep(64);        // rare: the hint counter said the words are on their way
             }
         };
         auto stage_x = [&]() {
