@@ -289,8 +289,6 @@ def main():
     ap.add_argument("--workload", default="llama7b_decode", choices=["llama7b_decode", "llama3_8b_prefill512"],
                     help="llama7b_decode = the headline (BASELINE.json metric / configs[1]); llama3_8b_prefill512 = config #5: "
                          "Llama-3-8B linear layers, a 512-token prompt per stream (prefill) + decode, one stream per GPU")
-    ap.add_argument("--order", default="program", choices=["program", "consumer-first"],
-                    help="diagnostic: order of the sibling layers inside a block (q,k,v / gate,up); the default is the model's")
     ap.add_argument("--chain", type=int, default=int(os.environ.get("B200BIT_CHAIN", "1")),
                     help="1: the token's 224 layer calls recorded into ONE decode-chain launch (DecodeChain.capture); "
                          "0: one launch per layer (programmatic dependent launch), as in round 1")
@@ -363,14 +361,9 @@ def main():
                 name, K, N, qw, sc, zr, gi = layer
                 return q_linear_cuda.mpq_forward(x, qw, sc, zr, gi, 16, W_BIT, False, pdl=pdl)
 
-            if args.order == "consumer-first":     # diagnostic: issue the sibling whose output the chain consumes first
-                v, q, k = fwd(hid, lv), fwd(hid, lq), fwd(hid, lk)
-                o = fwd(v, lo)
-                up, gate = fwd(o, lu), fwd(o, lg)
-            else:
-                q, k, v = fwd(hid, lq), fwd(hid, lk), fwd(hid, lv)      # all three stay alive, as attention needs them
-                o = fwd(v, lo)
-                gate, up = fwd(o, lg), fwd(o, lu)
+            q, k, v = fwd(hid, lq), fwd(hid, lk), fwd(hid, lv)      # all three stay alive, as attention needs them
+            o = fwd(v, lo)
+            gate, up = fwd(o, lg), fwd(o, lu)
             hid = fwd(up, ld)
             del q, k, gate
         return hid
@@ -471,7 +464,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": "llama7b_linear_layers_decode_bs1_w4_g128_sym", "layers_per_step": n_layers,
-                           "launches_per_step": n_launch, "decode_chain": int(use_chain), "sibling_order": args.order,
+                           "launches_per_step": n_launch, "decode_chain": int(use_chain),
                            "weights_bytes": tok_bytes, "l2_policy": "inputs (3.4 GB of distinct weights per step) "
                            "larger than L2", "parallelism": f"replicas x{world}", "pdl": int(pdl),
                            "dataflow": "llama decoder block: q,k,v <- hidden; o <- v (attention stand-in); "
