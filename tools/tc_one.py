@@ -14,3 +14,9 @@ for _ in range(3):
                                            y.data_ptr(), M, K, N, K // 128, 4, 0, _cabi.F16, None, 0, torch.cuda.current_stream().cuda_stream))
 torch.cuda.synchronize()
 print("ok")
+# the product route (workspace for split-K at small M comes from the shim)
+from bitorch_engine_b200.extensions import q_linear_cuda
+for _ in range(3):
+    y2 = q_linear_cuda.mpq_forward(inp["x"], inp["qweight"], inp["scales"], inp["zeros"], inp["g_idx"], 16, 4, False)
+torch.cuda.synchronize()
+print("shim ok", float((y2.float() - y.float()).abs().max()))
