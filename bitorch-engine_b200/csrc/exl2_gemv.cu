@@ -18,11 +18,12 @@
 // accumulation) and, in this repo's round 1, a dequantise + cuBLAS pair.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <type_traits>
 
 namespace b200bit {
 
 constexpr int EX_WARPS = 8;
-constexpr int EX_CHUNK = 256;              // weight rows staged per warp at a time (8 blocks of 32)
 struct Exl2Sections { int end[6]; int prow[6]; };   // section end (weight rows), first packed row; order 8,6,5,4,3,2
 
 struct Exl2Params {
@@ -34,67 +35,116 @@ struct Exl2Params {
     const __half* x;           // [M, K]
     __half* y;                 // [M, N]
     int M, K, N;
-    int blocks_per_warp;       // 32-row blocks per warp (k-slice)
+    int blocks_per_slice;      // 32-row blocks per k-slice
     Exl2Sections sec;
+};
+
+// MB rows of x per pass.  The eight warps of a CTA form WN column strips x WK k-slices: decode (MB <= 8) is latency-bound
+// and wants many short k-slices (1 x 8); at 16 / 32 rows the activations cost as much L2 traffic as the weights (they are
+// gathered through q_perm, one sector per value), so warps side by side share one staged copy (8 x 1 at 16 rows, 4 x 2 at
+// 32 rows, where twice the k-slices are needed to put two CTAs on every SM).
+// XB = 32-row blocks of x staged per k-slice at a time; D = blocks whose packed words are in flight per warp.
+template <int MB> struct ExCfg {
+    static constexpr int WN = MB <= 8 ? 1 : (MB == 16 ? 8 : 4);
+    static constexpr int WK = EX_WARPS / WN;
+    static constexpr int XB = MB <= 8 ? 8 : 4;
+    static constexpr int D = MB <= 8 ? 3 : (MB == 16 ? 2 : 1);
 };
 
 // 32 codes of width B from B consecutive words of one column -> fp16 bit patterns of 1024 + q, one per register
 template <int B>
-__device__ __forceinline__ void ex_unpack(const uint32_t (&w)[8], uint32_t (&h)[32]) {
+__device__ __forceinline__ void ex_unpack(const uint32_t (&w)[B], uint32_t (&h)[32]) {
     constexpr uint32_t mask = (1u << B) - 1u;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        constexpr int dummy = 0; (void)dummy;
         const int bit = j * B, i = bit >> 5, sh = bit & 31;
         uint32_t v;
         if (sh + B <= 32) v = w[i] >> sh;
-        else v = __funnelshift_r(w[i], w[i + 1], sh);
+        else v = __funnelshift_r(w[i], w[i + 1 < B ? i + 1 : i], sh);
         h[j] = (v & mask) | 0x6400u;
     }
 }
 
-template <int B, int MB>
-__device__ __forceinline__ void ex_block(const Exl2Params& p, int n, bool col_ok, int prow, int group, const uint4* xs,
-                                         const float* xsum, float (&yacc)[MB]) {
-    uint32_t w[8];
+// issue the loads of one block (32 weight rows, B packed rows) of column n; only the group index is waited for
+template <int B>
+__device__ __forceinline__ void ex_fetch(const Exl2Params& p, const uint32_t* src, int k, int n, bool col_ok, uint32_t (&w)[B],
+                                         unsigned short& s_raw, unsigned short& z_raw) {
+    const size_t stride = size_t(p.N);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = (i < B && col_ok) ? __ldg(p.qw + size_t(prow + i) * p.N + n) : 0u;
-    float s = 0.f, z = 0.f;
+    for (int i = 0; i < B; ++i) { w[i] = col_ok ? __ldg(src) : 0u; src += stride; }
+    const int group = __ldg(p.gmap + 2 * k);
+    s_raw = z_raw = 0;          // raw halves, untouched until the block is computed: nothing here may wait for them
     if (col_ok) {
-        s = __half2float(p.scales[size_t(group) * p.N + n]);
-        z = __half2float(p.zeros[size_t(group) * p.N + n]);
-    }
-    uint32_t h[32];
-    ex_unpack<B>(w, h);
-#pragma unroll
-    for (int m = 0; m < MB; ++m) {
-        float acc = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint4 xv = xs[m * (EX_CHUNK / 8) + q];        // 8 activations
-            const uint32_t xr[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                acc = fhfma<false, false, false>(h[8 * q + 2 * r], xr[r], acc);
-                acc = fhfma<false, false, true>(h[8 * q + 2 * r + 1], xr[r], acc);
-            }
-        }
-        yacc[m] = fmaf(s, acc, yacc[m]);
-        yacc[m] = fmaf(-(1024.f * s + z), xsum[m], yacc[m]);
+        const size_t at = size_t(group) * p.N + n;
+        s_raw = __ldg(reinterpret_cast<const unsigned short*>(p.scales) + at);
+        z_raw = __ldg(reinterpret_cast<const unsigned short*>(p.zeros) + at);
     }
 }
 
+// xs: the block's 32 activations of row m at xs + m * XSTRIDE halfs (16-byte aligned); xsum[m * XB]: their sum
+template <int B, int MB, int XSTRIDE, int XB>
+__device__ __forceinline__ void ex_block(const uint32_t (&w)[B], unsigned short s_raw, unsigned short z_raw, const __half* xs,
+                                         const float* xsum, float (&yacc)[MB]) {
+    uint32_t h[32];
+    ex_unpack<B>(w, h);
+    const float s = __half2float(__ushort_as_half(s_raw));
+    const float z = __half2float(__ushort_as_half(z_raw));
+    const float c = -(1024.f * s + z);
+    // MR rows at a time, two chains per row: the mixed-precision FMA has a long latency (~20 clk measured) and at 16 / 32
+    // rows only two warps share a scheduler, so the independent chains have to come from inside the warp
+    constexpr int MR = MB >= 4 ? 4 : MB;
+#pragma unroll
+    for (int m = 0; m < MB; m += MR) {
+        float a0[MR], a1[MR];
+#pragma unroll
+        for (int r = 0; r < MR; ++r) a0[r] = a1[r] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t xr[MR][4];
+#pragma unroll
+            for (int r = 0; r < MR; ++r) {
+                // 8 activations (same address in every lane: one broadcast wavefront)
+                const uint4 xv = reinterpret_cast<const uint4*>(xs + (m + r) * XSTRIDE)[q];
+                xr[r][0] = xv.x; xr[r][1] = xv.y; xr[r][2] = xv.z; xr[r][3] = xv.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int r = 0; r < MR; ++r) {
+                    a0[r] = fhfma<false, false, false>(h[8 * q + 2 * j], xr[r][j], a0[r]);
+                    a1[r] = fhfma<false, false, true>(h[8 * q + 2 * j + 1], xr[r][j], a1[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < MR; ++r) {
+            yacc[m + r] = fmaf(s, a0[r] + a1[r], yacc[m + r]);
+            yacc[m + r] = fmaf(c, xsum[(m + r) * XB], yacc[m + r]);
+        }
+    }
+}
+
+__device__ __forceinline__ void ex_group_sync(int id, int threads) {
+    if (threads == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 template <int MB>
-__global__ void __launch_bounds__(EX_WARPS * 32) exl2_gemv_kernel(const Exl2Params p) {
+__global__ void __launch_bounds__(EX_WARPS * 32, MB <= 2 ? 3 : 2) exl2_gemv_kernel(const Exl2Params p) {
+    constexpr int WN = ExCfg<MB>::WN, WK = ExCfg<MB>::WK, XB = ExCfg<MB>::XB, D = ExCfg<MB>::D, CH = XB * 32;
+    constexpr int COLS = WN * 32;
     extern __shared__ __align__(16) unsigned char ex_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = blockIdx.x * 32 + lane;
+    const int wn = warp % WN, wk = warp / WN;
+    const int gl = wn * 32 + lane;                       // thread index inside the k-slice group
+    const int n = blockIdx.x * COLS + gl;
     const bool col_ok = n < p.N;
     const int m0 = blockIdx.y * MB;
-    // per warp: x chunk [MB][256] halfs, block sums [MB][8] f32
-    __half* xs_w = reinterpret_cast<__half*>(ex_smem) + size_t(warp) * MB * EX_CHUNK;
-    float* xsum_w = reinterpret_cast<float*>(ex_smem + size_t(EX_WARPS) * MB * EX_CHUNK * sizeof(__half)) + warp * MB * 8;
-    float* red = reinterpret_cast<float*>(ex_smem + size_t(EX_WARPS) * MB * (EX_CHUNK * sizeof(__half) + 8 * sizeof(float)));
+    // per k-slice: x chunk [MB][CH] halfs, block sums [MB][XB] f32; then red [WK][MB][COLS] f32 (WK > 1), cta_sum [MB][COLS]
+    __half* xs_w = reinterpret_cast<__half*>(ex_smem) + size_t(wk) * MB * CH;
+    float* xsum_w = reinterpret_cast<float*>(ex_smem + size_t(WK) * MB * CH * sizeof(__half)) + wk * MB * XB;
+    float* red = reinterpret_cast<float*>(ex_smem + size_t(WK) * MB * (CH * sizeof(__half) + XB * sizeof(float)));
+    float* cta_sum = red + (WK > 1 ? WK * MB * COLS : 0);
 
     float yacc[MB];
 #pragma unroll
@@ -104,72 +154,105 @@ __global__ void __launch_bounds__(EX_WARPS * 32) exl2_gemv_kernel(const Exl2Para
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
     const int blocks_total = p.K / 32;
-    const int b_lo = (crank * EX_WARPS + warp) * p.blocks_per_warp;
-    const int b_hi = min(blocks_total, b_lo + p.blocks_per_warp);
-    for (int c0 = b_lo; c0 < b_hi; c0 += EX_CHUNK / 32) {
-        const int nblk = min(EX_CHUNK / 32, b_hi - c0);
-        // ---- stage the activations of the chunk (gathered through q_perm) + their per-block sums ----
-        __syncwarp();
-        for (int i = lane; i < MB * nblk * 32; i += 32) {
-            const int m = i / (nblk * 32), kl = i % (nblk * 32);
-            const int k = c0 * 32 + kl;
-            const int src = p.perm ? int(p.perm[k]) : k;
-            __half v = __float2half(0.f);
-            if (m0 + m < p.M) v = p.x[size_t(m0 + m) * p.K + src];
-            xs_w[m * EX_CHUNK + kl] = v;
-        }
-        __syncwarp();
-        for (int i = lane; i < MB * nblk; i += 32) {
-            const int m = i / nblk, b = i % nblk;
-            float sum = 0.f;
-            const __half2* src = reinterpret_cast<const __half2*>(xs_w + m * EX_CHUNK + b * 32);
+    const int b_lo = min(blocks_total, (crank * WK + wk) * p.blocks_per_slice);
+    const int b_hi = min(blocks_total, b_lo + p.blocks_per_slice);
+
+    // activations of blocks [b, b + nblk) of this k-slice (gathered through q_perm) + their per-block sums; executed by
+    // all WN warps of the slice
+    auto stage_x = [&](int b, int nblk) {
+        ex_group_sync(1 + wk, COLS);
+        for (int kl = gl; kl < nblk * 32; kl += COLS) {
+            const int k = b * 32 + kl;
+            const int src = p.perm ? int(__ldg(p.perm + k)) : k;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) { const float2 f = __half22float2(src[q]); sum += f.x + f.y; }
-            xsum_w[m * 8 + b] = sum;
-        }
-        __syncwarp();
-        for (int b = 0; b < nblk; ++b) {
-            const int blk = c0 + b, k = blk * 32;
-            int sec = 0;
-            while (sec < 5 && k >= p.sec.end[sec]) ++sec;
-            const int k_sec = sec == 0 ? 0 : p.sec.end[sec - 1];
-            const int widths[6] = {8, 6, 5, 4, 3, 2};
-            const int bits = widths[sec];
-            const int prow = p.sec.prow[sec] + (k - k_sec) / 32 * bits;
-            const int group = p.gmap[2 * k];
-            const uint4* xs = reinterpret_cast<const uint4*>(xs_w + b * 32);
-            float xsum[MB];
-#pragma unroll
-            for (int m = 0; m < MB; ++m) xsum[m] = xsum_w[m * 8 + b];
-            switch (bits) {
-                case 8: ex_block<8, MB>(p, n, col_ok, prow, group, xs, xsum, yacc); break;
-                case 6: ex_block<6, MB>(p, n, col_ok, prow, group, xs, xsum, yacc); break;
-                case 5: ex_block<5, MB>(p, n, col_ok, prow, group, xs, xsum, yacc); break;
-                case 4: ex_block<4, MB>(p, n, col_ok, prow, group, xs, xsum, yacc); break;
-                case 3: ex_block<3, MB>(p, n, col_ok, prow, group, xs, xsum, yacc); break;
-                default: ex_block<2, MB>(p, n, col_ok, prow, group, xs, xsum, yacc); break;
+            for (int m = 0; m < MB; ++m) {
+                __half v = __float2half(0.f);
+                if (m0 + m < p.M) v = p.x[size_t(m0 + m) * p.K + src];
+                xs_w[m * CH + kl] = v;
             }
         }
+        ex_group_sync(1 + wk, COLS);
+        for (int i = gl; i < MB * nblk; i += COLS) {
+            const int m = i / nblk, bb = i % nblk;
+            float sum = 0.f;
+            const __half2* src = reinterpret_cast<const __half2*>(xs_w + m * CH + bb * 32);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { const float2 f = __half22float2(src[q]); sum += f.x + f.y; }
+            xsum_w[m * XB + bb] = sum;
+        }
+        ex_group_sync(1 + wk, COLS);
+    };
+
+    // one section (constant bit width B) of the slice: software-pipelined, D blocks of packed words in flight
+    auto run = [&](auto btag, int s_lo, int s_hi, int k_sec, int prow0) {
+        constexpr int B = decltype(btag)::value;
+        uint32_t w[D][B];
+        unsigned short sr[D], zr[D];
+        const uint32_t* ptr = p.qw + size_t(prow0 + ((s_lo * 32 - k_sec) >> 5) * B) * p.N + n;
+        const size_t bstride = size_t(B) * p.N;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            sr[d] = zr[d] = 0;
+#pragma unroll
+            for (int i = 0; i < B; ++i) w[d][i] = 0u;
+            if (s_lo + d < s_hi) ex_fetch<B>(p, ptr + d * bstride, (s_lo + d) * 32, n, col_ok, w[d], sr[d], zr[d]);
+        }
+        for (int base = s_lo; base < s_hi; base += D) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const int b = base + d;
+                if (b < s_hi) {
+                    const int bl = (b - b_lo) % XB;
+                    if (bl == 0) stage_x(b, min(XB, b_hi - b));
+                    uint32_t cw[B];
+#pragma unroll
+                    for (int i = 0; i < B; ++i) cw[i] = w[d][i];
+                    const unsigned short cs = sr[d], cz = zr[d];
+                    if (b + D < s_hi)      // refill the slot: in flight during the FMAs below
+                        ex_fetch<B>(p, ptr + size_t(b + D - s_lo) * bstride, (b + D) * 32, n, col_ok, w[d], sr[d], zr[d]);
+                    ex_block<B, MB, CH, XB>(cw, cs, cz, xs_w + bl * 32, xsum_w + bl, yacc);
+                }
+            }
+        }
+    };
+    {
+        int k_sec = 0;
+#pragma unroll
+        for (int sec = 0; sec < 6; ++sec) {          // static indices: the section table stays in the constant bank
+            const int s_lo = max(b_lo, k_sec >> 5), s_hi = min(b_hi, p.sec.end[sec] >> 5);
+            if (s_lo < s_hi) {
+                if (sec == 0) run(std::integral_constant<int, 8>{}, s_lo, s_hi, k_sec, p.sec.prow[sec]);
+                else if (sec == 1) run(std::integral_constant<int, 6>{}, s_lo, s_hi, k_sec, p.sec.prow[sec]);
+                else if (sec == 2) run(std::integral_constant<int, 5>{}, s_lo, s_hi, k_sec, p.sec.prow[sec]);
+                else if (sec == 3) run(std::integral_constant<int, 4>{}, s_lo, s_hi, k_sec, p.sec.prow[sec]);
+                else if (sec == 4) run(std::integral_constant<int, 3>{}, s_lo, s_hi, k_sec, p.sec.prow[sec]);
+                else run(std::integral_constant<int, 2>{}, s_lo, s_hi, k_sec, p.sec.prow[sec]);
+            }
+            k_sec = p.sec.end[sec];
+        }
     }
-    // ---- the eight k-slices of the CTA meet in shared memory, then the CTAs of the cluster in rank order ----
+    // ---- the k-slices of the CTA meet in shared memory, then the CTAs of the cluster in rank order ----
+    if constexpr (WK > 1) {
 #pragma unroll
-    for (int m = 0; m < MB; ++m) red[(warp * MB + m) * 32 + lane] = yacc[m];
-    __syncthreads();
-    float* cta_sum = red + EX_WARPS * MB * 32;             // [MB][32]
-    for (int i = threadIdx.x; i < MB * 32; i += EX_WARPS * 32) {
-        const int m = i / 32, l = i % 32;
-        float t = 0.f;
+        for (int m = 0; m < MB; ++m) red[(wk * MB + m) * COLS + gl] = yacc[m];
+        __syncthreads();
+        for (int i = threadIdx.x; i < MB * COLS; i += EX_WARPS * 32) {
+            float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < EX_WARPS; ++w) t += red[(w * MB + m) * 32 + l];
-        cta_sum[i] = t;
+            for (int w = 0; w < WK; ++w) t += red[w * MB * COLS + i];
+            cta_sum[i] = t;
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < MB; ++m) cta_sum[m * COLS + gl] = yacc[m];
     }
     cluster.sync();
     if (crank == 0) {
-        for (int i = threadIdx.x; i < MB * 32; i += EX_WARPS * 32) {
-            const int m = i / 32, l = i % 32;
+        for (int i = threadIdx.x; i < MB * COLS; i += EX_WARPS * 32) {
+            const int m = i / COLS, l = i % COLS;
             float t = cta_sum[i];
             for (int r = 1; r < csize; ++r) t += cluster.map_shared_rank(cta_sum, r)[i];
-            const int col = blockIdx.x * 32 + l;
+            const int col = blockIdx.x * COLS + l;
             if (col < p.N && m0 + m < p.M) p.y[size_t(m0 + m) * p.N + col] = __float2half_rn(t);
         }
     }
@@ -178,15 +261,20 @@ __global__ void __launch_bounds__(EX_WARPS * 32) exl2_gemv_kernel(const Exl2Para
 
 template <int MB>
 static int launch_exl2(Exl2Params p, cudaStream_t st) {
-    const size_t smem = size_t(EX_WARPS) * MB * (EX_CHUNK * sizeof(__half) + 8 * sizeof(float)) +
-                        size_t(EX_WARPS + 1) * MB * 32 * sizeof(float);
+    constexpr int WN = ExCfg<MB>::WN, WK = ExCfg<MB>::WK, XB = ExCfg<MB>::XB, COLS = WN * 32;
+    const size_t smem = size_t(WK) * MB * (XB * 32 * sizeof(__half) + XB * sizeof(float)) +
+                        size_t((WK > 1 ? WK : 0) + 1) * MB * COLS * sizeof(float);
     auto kern = exl2_gemv_kernel<MB>;
     if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    // k-slices: 8 warps x cluster size; enough CTAs for ~3 per SM, at least 2 blocks of 32 rows per warp
-    const int blocks = p.K / 32, strips = (p.N + 31) / 32, mchunks = (p.M + MB - 1) / MB;
+    // k-slices: WK per CTA x cluster size -- as many as still fit ONE wave of CTAs (a second wave doubles the latency-bound
+    // run time: measured 11.3 vs 14.7 us at 4096^2, M = 1), at least 4 blocks of 32 rows per slice
+    const int blocks = p.K / 32, strips = (p.N + COLS - 1) / COLS, mchunks = (p.M + MB - 1) / MB;
     int csize = 1;
-    while (csize < 4 && strips * mchunks * csize < 3 * sm_count() && blocks >= 2 * EX_WARPS * csize * 2) csize *= 2;
-    p.blocks_per_warp = (blocks + EX_WARPS * csize - 1) / (EX_WARPS * csize);
+    const int max_c = WK > 2 ? 4 : 8;
+    while (csize < max_c && strips * mchunks * csize * 2 <= (12 * sm_count()) / 5 && blocks >= 2 * WK * csize * 2) csize *= 2;
+    static const int force_c = getenv("B200BIT_EXL2_CSIZE") ? atoi(getenv("B200BIT_EXL2_CSIZE")) : 0;     // sweep hook
+    if (force_c > 0 && force_c <= 8 && blocks >= WK * force_c) csize = force_c;
+    p.blocks_per_slice = (blocks + WK * csize - 1) / (WK * csize);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(strips, mchunks, csize);
     cfg.blockDim = dim3(EX_WARPS * 32, 1, 1);
@@ -238,5 +326,7 @@ extern "C" int b200bit_exl2_forward(const void* x, const int32_t* qweight, const
     if (M == 1) return launch_exl2<1>(p, st);
     if (M == 2) return launch_exl2<2>(p, st);
     if (M <= 4) return launch_exl2<4>(p, st);
-    return launch_exl2<8>(p, st);
+    if (M <= 8) return launch_exl2<8>(p, st);
+    if (M <= 16) return launch_exl2<16>(p, st);
+    return launch_exl2<32>(p, st);
 }
