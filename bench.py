@@ -274,11 +274,29 @@ def run_llama3(args, rank, world, dev):
                 "prefill": {"ms_per_prompt": ms_prefill / steps, "TFLOPs": flops / (ms_prefill / steps) / 1e9},
                 "decode": {"tokens_per_s": world * steps * NEW / (ms_decode / 1e3), "ms_per_token": ms_decode / steps / NEW},
                 "gpu_launches": steps * (len(layers) + NEW)}
-        print(json.dumps(line))
+        emit(line)
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line of the run, on the process's ORIGINAL stdout (see main: fd 1 itself is pointed at stderr so that
+    libraries printing to stdout -- NCCL's version banner -- cannot add lines to it)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -314,7 +332,7 @@ def main():
                 "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": cores, "kind": "port",
                                  "sample": sample},
                 "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -483,7 +501,7 @@ def main():
             tok_cpu, cores, sample, _ = run_cpu_arm(2, 1)
             line["cpu_baseline"] = {"value": tok_cpu, "unit": "tokens/s", "cores": cores, "kind": "port",
                                     "sample": sample}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

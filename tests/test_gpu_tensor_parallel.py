@@ -1,6 +1,5 @@
 """2-GPU check of the optional tensor-parallel wrappers (NCCL all-reduce / all-gather around the CUDA kernels).
-Needs two devices (`gpurun --gpus 2`) AND the opt-in B200BIT_TEST_TP=1: the wrappers have not been run on hardware yet
-(round 1 ended without a multi-GPU slot for it), so the default GPU suite does not depend on them."""
+Needs two devices (`gpurun --gpus 2`); passed on 2 x B200 in round 2 (tools/r2_gpu24.sh).  On a one-GPU box it skips."""
 import os
 
 import pytest
@@ -36,8 +35,8 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2 or os.environ.get("B200BIT_TEST_TP") != "1",
-                    reason="needs two GPUs and B200BIT_TEST_TP=1 (opt-in: not yet validated on hardware)")
+@pytest.mark.skipif(torch.cuda.device_count() < 2 or os.environ.get("B200BIT_TEST_TP") == "0",
+                    reason="needs two GPUs (B200BIT_TEST_TP=0 switches it off)")
 def test_two_gpu_row_and_column_parallel():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
