@@ -117,7 +117,7 @@ int b200bit_mpq_chain_build(const b200bit_chain_node* nodes, int n, int w_bit, i
     const int s_tile = gps * 64, z_tile = asym ? gps * 32 : gps * 64;
     const int sz_bytes = (s_tile + 127) & ~127;
     const int grid = max_strips < sms ? max_strips : sms;
-    const size_t fixed = size_t(IM_XIMG_BYTES) + (2 * IM_WARPS * 32) * sizeof(float) + size_t(n) * sizeof(ChainNode) +
+    const size_t fixed = size_t(IM_XIMG_BYTES) + size_t(CH_RED_FLOATS) * sizeof(float) + size_t(n) * sizeof(ChainNode) +
                          (2 * CH_MAX_STAGES + 5) * 8 + 64;
     static const int slot_cap = getenv("B200BIT_CHAIN_SLOTS") ? atoi(getenv("B200BIT_CHAIN_SLOTS")) : CH_MAX_STAGES;   // sweep hook
     int S = slot_cap < CH_MAX_STAGES ? (slot_cap < 2 ? 2 : slot_cap) : CH_MAX_STAGES;

@@ -36,6 +36,8 @@ constexpr int CH_MAX_STAGES = 7;
 constexpr int CH_SMEM_LIMIT = 227 * 1024;
 constexpr int CH_TRACE_NODES = 32;          // diagnostics: stamps for the first 32 nodes
 constexpr unsigned CH_SPIN_LIMIT = 1u << 22;   // polls before a wait gives up and raises the plan's error flag (~1 s)
+constexpr int CH_RED_PLANE = 33;                 // floats per (warp, value) plane of the hand-over buffer: 32 lanes + 1 pad (conflict-free reads)
+constexpr int CH_RED_FLOATS = IM_WARPS * 5 * CH_RED_PLANE;   // per warp: yacc[0..3] and yz of every lane
 constexpr int CH_THREADS = IM_THREADS + 128;   // sixteen compute warps + one helper warpgroup: the TMA producer warp, the epilogue /
                                                // dependency warp and two idle warps (register reallocation works on whole warpgroups)
 
@@ -158,13 +160,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
     const int S = p.S;
     const int grid = int(gridDim.x), bid = int(blockIdx.x);
     const int n_nodes = p.n_nodes;
-    // carve-up: W ring S x 28672 | scale / zero tiles S x 2 x sz_bytes | per-warp x digit images | red [2][16][32] f32 |
+    // carve-up: W ring S x 28672 | scale / zero tiles S x 2 x sz_bytes | per-warp x digit images | red [16][5][33] f32 |
     //           node table n x 64 | mbarriers full[7], empty[7], part[2], free[2], ready
     unsigned char* wst = ch_smem;
     unsigned char* szst = wst + size_t(S) * IM_TILE_BYTES;
     unsigned char* ximg = szst + size_t(S) * 2 * p.sz_bytes;
     float* red = reinterpret_cast<float*>(ximg + IM_XIMG_BYTES);
-    ChainNode* nodes_s = reinterpret_cast<ChainNode*>(red + 2 * IM_WARPS * 32);
+    ChainNode* nodes_s = reinterpret_cast<ChainNode*>(red + CH_RED_FLOATS);
     uint64_t* full = reinterpret_cast<uint64_t*>(nodes_s + n_nodes);   // [7] tile landed (TMA transaction bytes)
     uint64_t* empty = full + CH_MAX_STAGES;      // [7] the sixteen compute warps are done with the slot
     uint64_t* part = empty + CH_MAX_STAGES;      // [2] partial sums of a strip are in red[par]: 16 compute warps arrive
@@ -239,8 +241,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
         //       wait for each other or for a global-memory round trip: they hand their partial sums over through
         //       red[par] + an mbarrier and go on with the next strip. =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        unsigned use0 = 0u, use1 = 0u;           // how often red[0] / red[1] have been consumed
-        int par = 0, waited = -1;
+        unsigned use = 0u;                       // how often red has been consumed
+        int waited = -1;
+        // this lane's column of a strip: columns 2g, 2g + 1 are yacc[0], yacc[1] of the lane quad g, columns 16 + 2g, 17 + 2g
+        // are yacc[2], yacc[3]
+        const int eg = (lane & 15) >> 1, eq = (lane & 1) + ((lane >> 4) << 1);
         for (int node = next_node(0); node < n_nodes; node = next_node(node + 1)) {
             const ChainNode nd = nodes_s[node];
             if (nd.wx_node > waited) {       // read-after-write: the producer's counter (the ordering itself when x is plain,
@@ -260,17 +265,21 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
             }
             for (int strip = first_strip(nd); strip < nd.strips; strip += grid) {
                 const int n0 = strip_col(nd, strip);
-                const unsigned use = par ? use1 : use0;
-                ch_mbar_wait(smem_u32(&part[par]), use & 1u);
+                ch_mbar_wait(smem_u32(&part[0]), use & 1u);
                 if constexpr (TRACE) { if (p.trace && lane == 0 && node < CH_TRACE_NODES) p.trace[(size_t(bid) * CH_TRACE_NODES + node) * 8 + 0] = st_gtime(); }
-                const float* rd = red + par * (IM_WARPS * 32);
+                // the compute warps hand over their lanes' raw partial sums; the digit-pair lanes, the zero-point term and
+                // the sixteen warps are combined here, in the order of the per-layer kernel (bit-identical results)
                 float total = 0.f;
 #pragma unroll
-                for (int w = 0; w < IM_WARPS; ++w) total += rd[w * 32 + lane];
+                for (int w = 0; w < IM_WARPS; ++w) {
+                    const float* rw = red + w * 5 * CH_RED_PLANE;
+                    const float* rq = rw + eq * CH_RED_PLANE + eg * 4;
+                    const float t = (rq[0] + rq[1]) + (rq[2] + rq[3]);
+                    total += t - rw[4 * CH_RED_PLANE + eg * 4 + eq];
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&freeb[par]);
-                if (par) ++use1; else ++use0;
-                par ^= 1;
+                if (lane == 0) mbar_arrive(&freeb[0]);
+                ++use;
                 if (nd.wy_node >= 0) {       // write-after-read / write-after-write: the buffer behind y was used by node wy_node
                     if (lane == 0) ch_spin(p.counters + nd.wy_node, unsigned(nodes_s[nd.wy_node].strips), err_flag, true, p.poll_depth);
                     __syncwarp();
@@ -331,8 +340,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
     float yz = 0.f;
     int slot = 0;
     unsigned ph = 0;
-    int rd_par = 0;
-    unsigned dep_phase = 0u, use0 = 0u, use1 = 0u;
+    unsigned dep_phase = 0u, use = 0u;
     int waited = -1, prev_node = -2;
 
     for (int node = next_node(0); node < n_nodes; node = next_node(node + 1)) {
@@ -553,29 +561,24 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mpq_chain_kernel(const ChainPar
                 }
             }
             CH_TRACE(node, 2);
-            // ---- strip finished: digit-pair lanes, zero-point terms, then the sixteen warps in fixed order ----
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                yacc[q] += __shfl_xor_sync(0xffffffffu, yacc[q], 1);
-                yacc[q] += __shfl_xor_sync(0xffffffffu, yacc[q], 2);
-                yacc[q] -= __shfl_sync(0xffffffffu, yz, (lane & ~3) + q);
-            }
+            // ---- strip finished: the lanes' raw partial sums go to the epilogue warp as they are (five conflict-free stores;
+            //      the shuffle tree over the digit-pair lanes and the zero-point term moved there: ~60 fewer instructions per
+            //      strip in each of the sixteen warps that set the pace of every K = 4096 layer) ----
             {
-                // red[par] is free again once the epilogue warp has read its previous contents (two strips ago)
-                const unsigned use = rd_par ? use1 : use0;
-                if (use > 0u) ch_mbar_wait(smem_u32(&freeb[rd_par]), (use - 1u) & 1u);
-                if (rd_par) ++use1; else ++use0;
+                // red is free again once the epilogue warp has read the previous strip
+                if (use > 0u) ch_mbar_wait(smem_u32(&freeb[0]), (use - 1u) & 1u);
+                ++use;
             }
-            float* rd = red + rd_par * (IM_WARPS * 32);
-            if (c == 0) {
-                *reinterpret_cast<float2*>(rd + warp * 32 + 2 * g) = make_float2(yacc[0], yacc[1]);
-                *reinterpret_cast<float2*>(rd + warp * 32 + 16 + 2 * g) = make_float2(yacc[2], yacc[3]);
-            }
+            float* rw = red + warp * 5 * CH_RED_PLANE + lane;
+            rw[0] = yacc[0];
+            rw[CH_RED_PLANE] = yacc[1];
+            rw[2 * CH_RED_PLANE] = yacc[2];
+            rw[3 * CH_RED_PLANE] = yacc[3];
+            rw[4 * CH_RED_PLANE] = yz;
             yacc[0] = yacc[1] = yacc[2] = yacc[3] = 0.f;
             yz = 0.f;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&part[rd_par]);
-            rd_par ^= 1;
+            if (lane == 0) mbar_arrive(&part[0]);
         }
     }
 }
