@@ -47,8 +47,10 @@ struct Exl2Params {
 template <int MB> struct ExCfg {
     static constexpr int WN = MB <= 8 ? 1 : (MB == 16 ? 8 : 4);
     static constexpr int WK = EX_WARPS / WN;
-    static constexpr int XB = MB <= 8 ? 8 : 4;
-    static constexpr int D = MB <= 8 ? 3 : (MB == 16 ? 2 : 1);
+    // decode: the whole k-slice of x in one staging pass (the gather through q_perm is two dependent round trips during
+    // which the warp issues nothing else: once per slice instead of once per 8 blocks)
+    static constexpr int XB = MB <= 2 ? 32 : (MB == 4 ? 16 : (MB == 8 ? 8 : 4));
+    static constexpr int D = MB <= 2 ? 4 : (MB <= 8 ? 3 : (MB == 16 ? 2 : 1));
 };
 
 // 32 codes of width B from B consecutive words of one column -> fp16 bit patterns of 1024 + q, one per register
