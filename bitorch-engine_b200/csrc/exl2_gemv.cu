@@ -47,10 +47,10 @@ struct Exl2Params {
 template <int MB> struct ExCfg {
     static constexpr int WN = MB <= 8 ? 1 : (MB == 16 ? 8 : 4);
     static constexpr int WK = EX_WARPS / WN;
-    // decode: the whole k-slice of x in one staging pass (the gather through q_perm is two dependent round trips during
-    // which the warp issues nothing else: once per slice instead of once per 8 blocks)
-    static constexpr int XB = MB <= 2 ? 32 : (MB == 4 ? 16 : (MB == 8 ? 8 : 4));
-    static constexpr int D = MB <= 2 ? 4 : (MB <= 8 ? 3 : (MB == 16 ? 2 : 1));
+    // (staging the whole k-slice of x at once + 4 blocks in flight was measured no better for decode: 11.6 / 24.3 / 30.2 us
+    // against 11.3 / 24.9 / 26.5 us on the three Llama-7B shapes)
+    static constexpr int XB = MB <= 8 ? 8 : 4;
+    static constexpr int D = MB <= 8 ? 3 : (MB == 16 ? 2 : 1);
 };
 
 // 32 codes of width B from B consecutive words of one column -> fp16 bit patterns of 1024 + q, one per register
