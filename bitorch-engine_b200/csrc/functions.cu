@@ -69,26 +69,32 @@ __global__ void __launch_bounds__(FN_THREADS) q4_unpack_kernel(const uint8_t* __
             o[0] = hi; o[1] = lo;
         }
     };
-    for (size_t it = size_t(blockIdx.x) * blockDim.x + threadIdx.x; it < items; it += stride) {
-        const uint2 p = *reinterpret_cast<const uint2*>(in + it * 8);
-        const uint32_t w[2] = {p.x, p.y};
-        uint32_t v[16];
+    // one (thread, step) = two packed bytes -> four codes = ONE 16-byte store, so that a warp's store instruction covers 512
+    // contiguous bytes (a thread that unpacks a whole 8-byte item writes 64 bytes of its own and every store instruction of
+    // the warp touches 32 half-filled sectors); four steps in flight per thread
+    const size_t pairs = items * 4;
+    const uint16_t* in2 = reinterpret_cast<const uint16_t*>(in);
+    for (size_t base = (size_t(blockIdx.x) * blockDim.x) * 4; base < pairs; base += stride * 4) {
+        uint32_t h[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t byte = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-            v[2 * j] = byte >> 4; v[2 * j + 1] = byte & 15u;
+        for (int u = 0; u < 4; ++u) {
+            const size_t it = base + size_t(u) * blockDim.x + threadIdx.x;
+            h[u] = it < pairs ? uint32_t(in2[it]) : 0u;
         }
-        if constexpr (SCALE) {
-            float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = float(int(v[j]) > 7 ? int(v[j]) - 16 : int(v[j])) * scale;
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + it * 16);
+        for (int u = 0; u < 4; ++u) {
+            const size_t it = base + size_t(u) * blockDim.x + threadIdx.x;
+            if (it >= pairs) continue;
+            const uint32_t b0 = h[u] & 0xffu, b1 = h[u] >> 8;
+            const uint32_t v[4] = {b0 >> 4, b0 & 15u, b1 >> 4, b1 & 15u};
+            if constexpr (SCALE) {
+                float f[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-        } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<int32_t*>(out_) + it * 16);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) o[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int j = 0; j < 4; ++j) f[j] = float(int(v[j]) > 7 ? int(v[j]) - 16 : int(v[j])) * scale;
+                reinterpret_cast<float4*>(out_)[it] = make_float4(f[0], f[1], f[2], f[3]);
+            } else {
+                reinterpret_cast<uint4*>(out_)[it] = make_uint4(v[0], v[1], v[2], v[3]);
+            }
         }
     }
     if (blockIdx.x == 0)
@@ -138,16 +144,14 @@ __global__ void __launch_bounds__(FN_THREADS) sign_pack_kernel(const void* __res
 // ---- sign unpack: byte -> eight +-scale floats; scale index = byte index / packed_dim (:128) ----
 __global__ void __launch_bounds__(FN_THREADS) sign_unpack_kernel(const uint8_t* __restrict__ in, const float* __restrict__ scale,
                                                                  float* __restrict__ out, size_t n_bytes, size_t packed_dim) {
+    // one (thread, step) = one nibble -> four floats = one 16-byte store (a warp's store instruction covers 512 contiguous bytes)
     const size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t b = size_t(blockIdx.x) * blockDim.x + threadIdx.x; b < n_bytes; b += stride) {
-        const uint32_t w = in[b];
+    const size_t halves = n_bytes * 2;
+    for (size_t it = size_t(blockIdx.x) * blockDim.x + threadIdx.x; it < halves; it += stride) {
+        const size_t b = it >> 1;
+        const uint32_t w = uint32_t(in[b]) >> ((it & 1) * 4);
         const float sc = scale[b / packed_dim];
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = ((w >> j) & 1u) ? sc : -sc;
-        float4* o = reinterpret_cast<float4*>(out + b * 8);
-        o[0] = make_float4(f[0], f[1], f[2], f[3]);
-        o[1] = make_float4(f[4], f[5], f[6], f[7]);
+        reinterpret_cast<float4*>(out)[it] = make_float4((w & 1u) ? sc : -sc, (w & 2u) ? sc : -sc, (w & 4u) ? sc : -sc, (w & 8u) ? sc : -sc);
     }
 }
 
@@ -212,7 +216,7 @@ int b200bit_sign_unpack_u8(const uint8_t* in, const float* scale, float* out, si
     B200_REQUIRE(packed_dim > 0, B200BIT_ERR_SHAPE, "sign_unpack_u8: packed_dim must be positive");
     B200_REQUIRE(aligned16(out), B200BIT_ERR_ARG, "sign_unpack_u8: out must be 16-byte aligned");
     if (n_bytes == 0) return B200BIT_OK;
-    sign_unpack_kernel<<<fn_grid(n_bytes), FN_THREADS, 0, st>>>(in, scale, out, n_bytes, packed_dim);
+    sign_unpack_kernel<<<fn_grid(n_bytes * 2), FN_THREADS, 0, st>>>(in, scale, out, n_bytes, packed_dim);
     B200_CUDA_OK(cudaGetLastError());
     return B200BIT_OK;
 }

@@ -137,19 +137,38 @@ __global__ void __launch_bounds__(256) diodemix_binary_kernel(int8_t* __restrict
                                                               void* __restrict__ s_, size_t numel, float w1, float w2,
                                                               float lr) {
     using C = OEl<CDT>;
-    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-    if (i >= numel) return;
-    const float g = grad_i8 ? float(grad_i8[i]) : C::ld(grad_c, i);
-    float m = C::rnd(lerp_torch(C::ld(m_, i), C::rnd(g), w1));
-    const float v = C::rnd(__fmul_rn(sgn(m), lr));
-    float s = C::rnd(lerp_torch(C::ld(s_, i), v, w2));
-    C::st(m_, i, m);
-    C::st(s_, i, s);
-    float u = -sgn(s);
-    if (u == 0.f) u = 1.f;
-    const int8_t wv = w[i];
-    const float sw = float((wv > 0) - (wv < 0));
-    if (u != sw) w[i] = int8_t(-wv);
+    // four elements per thread, one block-width apart (every load instruction of a warp stays contiguous): all twelve
+    // loads are in flight before the first result is needed
+    const size_t base = blockIdx.x * size_t(blockDim.x) * 4 + threadIdx.x;
+    float g4[4], m4[4], s4[4];
+    int8_t w4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const size_t i = base + size_t(u) * blockDim.x;
+        g4[u] = m4[u] = s4[u] = 0.f;
+        w4[u] = 0;
+        if (i < numel) {
+            g4[u] = grad_i8 ? float(grad_i8[i]) : C::ld(grad_c, i);
+            m4[u] = C::ld(m_, i);
+            s4[u] = C::ld(s_, i);
+            w4[u] = w[i];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const size_t i = base + size_t(u) * blockDim.x;
+        if (i >= numel) continue;
+        const float m = C::rnd(lerp_torch(m4[u], C::rnd(g4[u]), w1));
+        const float v = C::rnd(__fmul_rn(sgn(m), lr));
+        const float s = C::rnd(lerp_torch(s4[u], v, w2));
+        C::st(m_, i, m);
+        C::st(s_, i, s);
+        float uu = -sgn(s);
+        if (uu == 0.f) uu = 1.f;
+        const int8_t wv = w4[u];
+        const float sw = float((wv > 0) - (wv < 0));
+        if (uu != sw) w[i] = int8_t(-wv);
+    }
 }
 
 }  // namespace b200bit
@@ -204,7 +223,7 @@ int b200bit_diodemix_binary_step(int8_t* weight, const int8_t* grad_i8, const vo
     B200_REQUIRE(weight && (grad_i8 || grad_c) && exp_avg_l && exp_avg_s, B200BIT_ERR_ARG,
                  "diodemix_binary_step: null pointer argument");
     if (numel == 0) return B200BIT_OK;
-    const unsigned blocks = unsigned((numel + 255) / 256);
+    const unsigned blocks = unsigned((numel + 1023) / 1024);
     const float w1 = float(1.0 - beta1), w2 = float(1.0 - beta2), lrf = float(lr);
     if (compute_dtype == B200BIT_F32) diodemix_binary_kernel<B200BIT_F32><<<blocks, 256, 0, st>>>(weight, grad_i8, grad_c, exp_avg_l, exp_avg_s, numel, w1, w2, lrf);
     else if (compute_dtype == B200BIT_F16) diodemix_binary_kernel<B200BIT_F16><<<blocks, 256, 0, st>>>(weight, grad_i8, grad_c, exp_avg_l, exp_avg_s, numel, w1, w2, lrf);
