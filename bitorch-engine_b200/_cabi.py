@@ -38,7 +38,7 @@ PROTOTYPES = {
     "b200bit_mpq_grad_input": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p]),
     "b200bit_mpq_dequant": (_c_int, [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p, _c_void_p]),
     "b200bit_exl2_dequant": (_c_int, [_c_void_p] * 6 + [_c_int, _c_int, ctypes.POINTER(_c_int), _c_void_p]),
-    "b200bit_exl2_forward": (_c_int, [_c_void_p] * 7 + [_c_int, _c_int, _c_int, ctypes.POINTER(_c_int), _c_void_p]),
+    "b200bit_exl2_forward": (_c_int, [_c_void_p] * 7 + [_c_int, _c_int, _c_int, _c_int, ctypes.POINTER(_c_int), _c_void_p]),
     "b200bit_mpq_pack_weight": (_c_int, [_c_void_p] * 6 + [_c_int] * 8 + [_c_void_p]),
     "b200bit_diodemix_mpq_step": (_c_int, [_c_void_p] * 6 + [_c_int] * 8 + [ctypes.c_double] * 4 + [_c_int, _c_void_p]),
     "b200bit_diodemix_binary_step": (_c_int, [_c_void_p] * 5 + [_c_size_t, _c_int] + [ctypes.c_double] * 3 + [_c_void_p]),

@@ -386,7 +386,7 @@ def mbwq_exl2_forward(x, qweight, scales, zeros, q_perm, q_group_map, rows, use_
     with _on_device(x.device):
         rc = _cabi.lib().b200bit_exl2_forward(x.contiguous().data_ptr(), qweight.contiguous().data_ptr(),
                                               scales.contiguous().data_ptr(), zeros.contiguous().data_ptr(), _ptr(perm),
-                                              q_group_map.contiguous().data_ptr(), y.data_ptr(), M, K, N, rows6,
+                                              q_group_map.contiguous().data_ptr(), y.data_ptr(), M, K, N, int(scales.shape[0]), rows6,
                                               _raw_stream(x.device))
     if rc:
         _cabi.check(rc)

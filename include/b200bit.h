@@ -160,9 +160,10 @@ B200BIT_API int b200bit_exl2_dequant(const int32_t* qweight, const void* scales,
 /* Fused exl2 mixed bit-width forward: y[M,N] = x[:, perm] @ W without materialising W (fp16; fp32 accumulation; M rows
  * through the grid, no cuBLAS).  Replaces mbwq_exl2_forward -> gemm_half_q_half_kernel (q_linear_cuda.cpp:338-354,
  * mbwq_linear_cuda_kernel.cu:926-1007, exl2/q_gemm_kernel.cuh:90-549).  rows6_host as for b200bit_exl2_dequant; groups
- * must be runs of 32*i weight rows (the exl2 packing guarantees it). */
+ * must be runs of 32*i weight rows (the exl2 packing guarantees it); G = rows of the scales / zeros tables.  Up to 4 rows
+ * the packed rows stream through a TMA ring (one tensor map per bit width), 5 - 32 rows use register-prefetched loads. */
 B200BIT_API int b200bit_exl2_forward(const void* x, const int32_t* qweight, const void* scales, const void* zeros,
-                                     const int16_t* perm, const int16_t* q_group_map, void* y, int M, int K, int N,
+                                     const int16_t* perm, const int16_t* q_group_map, void* y, int M, int K, int N, int G,
                                      const int* rows6_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
