@@ -33,6 +33,7 @@ PROTOTYPES = {
     "b200bit_mpq_chain_build": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_size_t,
                                          ctypes.POINTER(_c_int)]),
     "b200bit_mpq_chain_launch": (_c_int, [_c_void_p, ctypes.POINTER(_c_int), _c_uint, _c_void_p]),
+    "b200bit_mpq_chain_plan_host": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, ctypes.POINTER(_c_int)]),
     "b200bit_mpq_chain_status": (_c_int, [_c_void_p, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), _c_void_p]),
     "b200bit_mpq_forward_tc": (_c_int, [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p, _c_size_t, _c_void_p]),
     "b200bit_mpq_grad_input": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p]),
@@ -60,6 +61,13 @@ class ChainNode(ctypes.Structure):
     """b200bit_chain_node (include/b200bit.h)."""
     _fields_ = [("x", _c_void_p), ("y", _c_void_p), ("qweight", _c_void_p), ("scales", _c_void_p), ("zeros", _c_void_p),
                 ("K", _c_int), ("N", _c_int), ("G", _c_int), ("reserved", _c_int)]
+
+
+class ChainPlanNode(ctypes.Structure):
+    """One 64-byte record of the plan's node table (csrc/mpq_chain.cuh ChainNode), as b200bit_mpq_chain_plan_host writes it."""
+    _fields_ = [("x", _c_void_p), ("y", _c_void_p), ("xll", _c_void_p), ("yll", _c_void_p), ("R", _c_int), ("N", _c_int),
+                ("strips", _c_int), ("n28", _c_int), ("tiles", _c_int), ("off_sig", _c_int), ("wx_node", _c_int),
+                ("wy_node", _c_int)]
 
 
 _lib = None

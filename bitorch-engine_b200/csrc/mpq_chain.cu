@@ -82,8 +82,10 @@ size_t b200bit_mpq_chain_plan_bytes(const b200bit_chain_node* nodes, int n_nodes
     return (nodes && n_nodes > 0) ? chain_plan_bytes(nodes, n_nodes) : 0;
 }
 
-int b200bit_mpq_chain_build(const b200bit_chain_node* nodes, int n, int w_bit, int asym, int dtype, void* plan_device,
-                            size_t plan_bytes, int* info16) {
+// host_only != nullptr: planning only (hazards, strip deal, shadow assignment) into a host array of n 64-byte node records --
+// no tensor maps, nothing touches the device; the shadow pointers are offsets from `plan_device` (any non-null base)
+static int chain_build(const b200bit_chain_node* nodes, int n, int w_bit, int asym, int dtype, void* plan_device,
+                       size_t plan_bytes, int* info16, void* host_only) {
     B200_REQUIRE(nodes && plan_device && info16, B200BIT_ERR_ARG, "mpq_chain_build: null pointer argument");
     B200_REQUIRE(n > 0 && n <= 4096, B200BIT_ERR_SHAPE, "mpq_chain_build: %d nodes (1..4096)", n);
     B200_REQUIRE(w_bit == 4, B200BIT_ERR_UNSUPPORTED, "mpq_chain_build: w_bit=%d (the decode chain is the 4-bit kernel)", w_bit);
@@ -183,23 +185,32 @@ int b200bit_mpq_chain_build(const b200bit_chain_node* nodes, int n, int w_bit, i
         if (c.wy_node >= 0) cn[c.wy_node].off_sig |= 1 << 20;
         if (i > 0 && nodes[i - 1].x == nd.x && nodes[i - 1].K == nd.K) c.off_sig |= 1 << 22;      // sibling: same x
         if (c.wx_node > max_wait) max_wait = c.wx_node;
-        int rc = make_map_2d(&maps[3 * i], CU_TENSOR_MAP_DATA_TYPE_UINT32, nd.qweight, uint64_t(nd.N), uint64_t(nd.K / 8),
-                             uint64_t(nd.N) * 4, IM_COLS, IM_TILE_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE);
-        if (rc != B200BIT_OK) return rc;
-        rc = make_map_2d(&maps[3 * i + 1], CU_TENSOR_MAP_DATA_TYPE_UINT16, nd.scales, uint64_t(nd.N), uint64_t(nd.G),
-                         uint64_t(nd.N) * 2, 32, uint32_t(gps), CU_TENSOR_MAP_SWIZZLE_NONE);
-        if (rc != B200BIT_OK) return rc;
-        if (asym)
-            rc = make_map_2d(&maps[3 * i + 2], CU_TENSOR_MAP_DATA_TYPE_UINT32, nd.zeros, uint64_t(nd.N / 8), uint64_t(nd.G),
-                             uint64_t(nd.N / 8) * 4, 8, uint32_t(gps), CU_TENSOR_MAP_SWIZZLE_NONE);
-        else
-            rc = make_map_2d(&maps[3 * i + 2], CU_TENSOR_MAP_DATA_TYPE_UINT16, nd.zeros, uint64_t(nd.N), uint64_t(nd.G),
+    }
+    if (host_only) {
+        memcpy(host_only, image.data(), size_t(n) * sizeof(ChainNode));
+    } else {
+        for (int i = 0; i < n; ++i) {
+            const b200bit_chain_node& nd = nodes[i];
+            int rc = make_map_2d(&maps[3 * i], CU_TENSOR_MAP_DATA_TYPE_UINT32, nd.qweight, uint64_t(nd.N), uint64_t(nd.K / 8),
+                                 uint64_t(nd.N) * 4, IM_COLS, IM_TILE_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc != B200BIT_OK) return rc;
+            rc = make_map_2d(&maps[3 * i + 1], CU_TENSOR_MAP_DATA_TYPE_UINT16, nd.scales, uint64_t(nd.N), uint64_t(nd.G),
                              uint64_t(nd.N) * 2, 32, uint32_t(gps), CU_TENSOR_MAP_SWIZZLE_NONE);
-        if (rc != B200BIT_OK) return rc;
+            if (rc != B200BIT_OK) return rc;
+            if (asym)
+                rc = make_map_2d(&maps[3 * i + 2], CU_TENSOR_MAP_DATA_TYPE_UINT32, nd.zeros, uint64_t(nd.N / 8), uint64_t(nd.G),
+                                 uint64_t(nd.N / 8) * 4, 8, uint32_t(gps), CU_TENSOR_MAP_SWIZZLE_NONE);
+            else
+                rc = make_map_2d(&maps[3 * i + 2], CU_TENSOR_MAP_DATA_TYPE_UINT16, nd.zeros, uint64_t(nd.N), uint64_t(nd.G),
+                                 uint64_t(nd.N) * 2, 32, uint32_t(gps), CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc != B200BIT_OK) return rc;
+        }
     }
     reinterpret_cast<unsigned*>(image.data() + chain_counters_offset(n))[n + 2] = 1u;      // first launch epoch
-    B200_CUDA_OK(cudaMemcpy(plan_device, image.data(), image.size(), cudaMemcpyHostToDevice));
-    B200_CUDA_OK(cudaMemset(dev_base + chain_shadow_offset(n), 0, shadow_at - chain_shadow_offset(n)));
+    if (!host_only) {
+        B200_CUDA_OK(cudaMemcpy(plan_device, image.data(), image.size(), cudaMemcpyHostToDevice));
+        B200_CUDA_OK(cudaMemset(dev_base + chain_shadow_offset(n), 0, shadow_at - chain_shadow_offset(n)));
+    }
     memset(info16, 0, 16 * sizeof(int));
     info16[CI_MAGIC] = CHAIN_MAGIC; info16[CI_NODES] = n; info16[CI_GRID] = grid; info16[CI_S] = S; info16[CI_F] = F;
     info16[CI_ASYM] = asym ? 1 : 0; info16[CI_BF16] = dtype == B200BIT_BF16 ? 1 : 0;
@@ -207,6 +218,18 @@ int b200bit_mpq_chain_build(const b200bit_chain_node* nodes, int n, int w_bit, i
     info16[CI_RPG_SHIFT] = rpg_shift; info16[CI_SZ] = sz_bytes; info16[CI_STILE] = s_tile; info16[CI_ZTILE] = z_tile;
     info16[CI_MAX_WAIT] = max_wait;
     return B200BIT_OK;
+}
+
+int b200bit_mpq_chain_build(const b200bit_chain_node* nodes, int n, int w_bit, int asym, int dtype, void* plan_device,
+                            size_t plan_bytes, int* info16) {
+    return chain_build(nodes, n, w_bit, asym, dtype, plan_device, plan_bytes, info16, nullptr);
+}
+
+int b200bit_mpq_chain_plan_host(const b200bit_chain_node* nodes, int n, int w_bit, int asym, int dtype, void* node_table_host,
+                                int* info16) {
+    B200_REQUIRE(node_table_host != nullptr, B200BIT_ERR_ARG, "mpq_chain_plan_host: null output");
+    // a fake, aligned, never dereferenced base: shadow pointers in the table are base + offset
+    return chain_build(nodes, n, w_bit, asym, dtype, reinterpret_cast<void*>(uintptr_t(1) << 20), ~size_t(0), info16, node_table_host);
 }
 
 int b200bit_mpq_chain_launch(void* plan_device, const int* info16, unsigned flags, void* stream_) {

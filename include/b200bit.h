@@ -127,6 +127,11 @@ typedef struct {
 B200BIT_API size_t b200bit_mpq_chain_plan_bytes(const b200bit_chain_node* nodes_host, int n_nodes);
 B200BIT_API int b200bit_mpq_chain_build(const b200bit_chain_node* nodes_host, int n_nodes, int w_bit, int asym, int dtype,
                                         void* plan_device, size_t plan_bytes, int* info16_host);
+/* Planning only, on the host, no device needed (diagnostics / tests): writes the n 64-byte node records of the plan --
+ * {x, y, xll, yll (pointers; shadows as offsets from a fake base), R, N, strips, n28, tiles, off_sig, wx_node, wy_node},
+ * see csrc/mpq_chain.cuh -- and info16.  Assumes 148 SMs when no device is present. */
+B200BIT_API int b200bit_mpq_chain_plan_host(const b200bit_chain_node* nodes_host, int n_nodes, int w_bit, int asym, int dtype,
+                                            void* node_table_host, int* info16_host);
 B200BIT_API int b200bit_mpq_chain_launch(void* plan_device, const int* info16_host, unsigned flags, void* stream);
 B200BIT_API int b200bit_mpq_chain_status(const void* plan_device, const int* info16_host, int* error_flag_host, void* stream);
 
