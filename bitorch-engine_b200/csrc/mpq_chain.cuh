@@ -12,10 +12,11 @@
 //     of HBM time.
 //   * dependencies travel WITH the data: a node whose output feeds a later node also writes it as 8-byte words
 //     {two 16-bit values, launch epoch} into a shadow buffer ("LL" protocol: a naturally aligned 64-bit store is
-//     single-copy atomic, so a reader that sees the epoch sees the values -- no fence, no flag round trip).  The consumer's
-//     warps read their own rows of x from the shadow and simply retry until every word carries this launch's epoch.
-//     A fence.gpu on an SM that has 150 KB of TMA loads in flight costs ~1.5 us (measured, profiles/r2_02_*), which is
-//     why the counter protocol below is only the fallback.
+//     single-copy atomic, so a reader that sees the epoch sees the values -- no fence).  A relaxed per-node counter is
+//     the HINT that pulling is worth it: the dependency warp polls it and releases the compute warps once half of the
+//     producer's strips are counted (early_pct); they read their own rows of x from the shadow and simply retry the rows
+//     whose words do not carry this launch's epoch yet.  A fence.gpu on an SM that has 150 KB of TMA loads in flight
+//     costs ~1.5 us (measured, profiles/r2_02_*), which is why the counter protocol below is only the fallback.
 //   * fallback for everything that is not "x is exactly an earlier node's y": counters in global memory.  The CTA that
 //     has written a strip of y does red.release.gpu on the node's counter; a dependent polls it (one lane per CTA,
 //     ld.acquire.gpu, bounded spin).  The host derives the hazards from the pointer ranges: read-after-write before x
@@ -103,10 +104,9 @@ __device__ __forceinline__ unsigned ch_ld_relaxed(const unsigned* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// Wait until *ctr >= want.  A loaded L2 round trip is ~1 us while the weight stream is running, so the polls are
-// PIPELINED: four relaxed loads in flight -- the counter's final value is seen one round trip after it lands instead of
-// 1.5 on average.  `ordered`: the counter orders plain memory (acquire fence at the end); otherwise it
-// is only a hint and the data validates itself.
+// Wait until *ctr >= want.  A loaded L2 round trip is 0.5 - 1 us while the weight stream is running; `depth` polls can be
+// kept in flight (1, 2 or 4; measured equal on the final build, default 1).  `ordered`: the counter orders plain memory
+// (acquire fence at the end); otherwise it is only a hint and the data validates itself.
 __device__ __forceinline__ void ch_spin(const unsigned* ctr, unsigned want, unsigned* err, bool ordered, int depth) {
     unsigned a = ch_ld_relaxed(ctr);
     if (a < want) {
