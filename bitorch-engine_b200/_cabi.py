@@ -35,6 +35,7 @@ PROTOTYPES = {
     "b200bit_mpq_chain_launch": (_c_int, [_c_void_p, ctypes.POINTER(_c_int), _c_uint, _c_void_p]),
     "b200bit_mpq_chain_plan_host": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, ctypes.POINTER(_c_int)]),
     "b200bit_mpq_chain_status": (_c_int, [_c_void_p, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), _c_void_p]),
+    "b200bit_mpq_forward_tc_supported": (_c_int, [_c_int] * 7 + [_c_size_t]),
     "b200bit_mpq_forward_tc": (_c_int, [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p, _c_size_t, _c_void_p]),
     "b200bit_mpq_grad_input": (_c_int, [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p]),
     "b200bit_mpq_dequant": (_c_int, [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p, _c_void_p]),

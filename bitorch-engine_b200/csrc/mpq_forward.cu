@@ -783,7 +783,7 @@ int b200bit_mpq_forward(const void* x, const int32_t* qweight, const void* scale
     // ---- more than 16 rows: tcgen05 batched kernel (mpq_tc.cu), one pass over the packed matrix ----
     if (M > (g_path == 5 ? 0 : (w_bit == 2 ? 8 : 16)) && (g_path == 0 || g_path == 5) && trivial && (w_bit == 4 || w_bit == 2) && dtype == B200BIT_F16 && K % 64 == 0 && N % 8 == 0 &&
         K % G == 0 && (K / G) % 32 == 0 && ((K / G) & (K / G - 1)) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-        size_t(G) * (asym ? 320 : 512) <= size_t(160) * 1024)
+        b200bit_mpq_forward_tc_supported(M, K, N, G, w_bit, asym, dtype, workspace ? workspace_bytes : 0))
         return b200bit_mpq_forward_tc(x, qweight, scales, zeros, y, M, K, N, G, w_bit, asym, dtype, workspace, workspace_bytes, stream_);
     // ---- path selection: TMA-streamed tensor kernel (f16, M <= 32) > mma.sync kernel > CUDA-core GEMV > general ----
     // auto: M == 1 -> CUDA-core FHFMA GEMV (fastest measured at batch 1, profiles/r1_*); 2 <= M: TMA-streamed tensor kernel

@@ -41,6 +41,7 @@ struct TcParams {
     uint16_t* y;              // [M, N] f16
     int M, K, N, G;
     int gs, gs_shift;         // group size (k) = 1 << gs_shift
+    int Gs;                   // rows of the shared-memory group table: most groups any one k-slice touches
     int splits;               // split-K factor (grid.z): > 1 when the tiles alone would leave most SMs idle (small M)
     float* part;              // [splits][M][N] fp32 partial results (splits > 1)
     unsigned* tickets;        // [tiles] zero-initialised, self-resetting (splits > 1)
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
     // group parameters of the CTA's 128 columns, all groups: scales [G][128] f16 | zeros [G][128] f16 (sym) or [G][16] packed
     // words (asym).  Staged once: a global load per group change sat on the dequant warps' critical path (~1 us each).
     uint16_t* s_sm = reinterpret_cast<uint16_t*>(tc_smem + TC_XSTAGES * TC_X_STAGE_BYTES + 256);
-    unsigned char* z_sm = reinterpret_cast<unsigned char*>(s_sm + size_t(p.G) * TC_BN);
+    unsigned char* z_sm = reinterpret_cast<unsigned char*>(s_sm + size_t(p.Gs) * TC_BN);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
@@ -142,6 +143,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
     const int stages_all = p.K / TC_KS;
     const int s_beg = int((long long)stages_all * blockIdx.z / p.splits), s_end = int((long long)stages_all * (blockIdx.z + 1) / p.splits);
     const int stages = s_end - s_beg;
+    // only the groups this CTA's k-range touches are staged (split-K keeps the table small: 344 groups of a 2-bit g32
+    // 11008-row layer would not fit as a whole)
+    const int g_lo = (s_beg * TC_KS) >> p.gs_shift;
+    const int g_cnt = stages > 0 ? (((s_end * TC_KS - 1) >> p.gs_shift) - g_lo + 1) : 0;
 
     if (tid == 0) {
         for (int i = 0; i < TC_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
@@ -153,15 +158,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < p.G * TC_BN; i += TC_THREADS) {
-        const int g = i / TC_BN, c = i % TC_BN;
+    for (int i = tid; i < g_cnt * TC_BN; i += TC_THREADS) {
+        const int g = g_lo + i / TC_BN, c = i % TC_BN;
         const int col = n0 + c;
         s_sm[i] = col < p.N ? p.scales[size_t(g) * p.N + col] : uint16_t(0);
         if (!p.asym) reinterpret_cast<uint16_t*>(z_sm)[i] = col < p.N ? reinterpret_cast<const uint16_t*>(p.zeros)[size_t(g) * p.N + col] : uint16_t(0);
     }
     if (p.asym)
-        for (int i = tid; i < p.G * (TC_BN / NB); i += TC_THREADS) {
-            const int g = i / (TC_BN / NB), c = i % (TC_BN / NB);
+        for (int i = tid; i < g_cnt * (TC_BN / NB); i += TC_THREADS) {
+            const int g = g_lo + i / (TC_BN / NB), c = i % (TC_BN / NB);
             const int wcol = n0 / NB + c;
             reinterpret_cast<uint32_t*>(z_sm)[i] = wcol < p.N / NB ? reinterpret_cast<const uint32_t*>(p.zeros)[size_t(g) * (p.N / NB) + wcol] : 0u;
         }
@@ -227,7 +232,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
         uint32_t s512 = 0u, mz = 0u;
         const int cl = q4 * 32 + lane;                 // column inside the CTA's tile
         int use = 0;                                   // how often the group's A slot has been filled
-        auto group_params = [&](int g, uint32_t& s2, uint32_t& z2) {
+        auto group_params = [&](int g_abs, uint32_t& s2, uint32_t& z2) {
+            const int g = g_abs - g_lo;
             const float sf = __half2float(__ushort_as_half(s_sm[g * TC_BN + cl]));
             float zf;
             if (p.asym) zf = sf * float(((reinterpret_cast<const uint32_t*>(z_sm)[g * (TC_BN / NB) + cl / NB] >> ((cl % NB) * BITS)) & ((1u << BITS) - 1u)) + 1u);
@@ -336,6 +342,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mpq_tc_kernel(const __grid_cons
 
 using namespace b200bit;
 
+namespace b200bit {
+struct TcPlan { int BM, tiles, stages, splits, Gs; size_t smem; bool fits; };
+// tile height, split-K factor, rows of the group table and shared memory of a launch (pure host arithmetic)
+static TcPlan tc_plan(int M, int K, int N, int G, int w_bit, int asym, size_t workspace_bytes) {
+    TcPlan pl{};
+    const int tiles128 = ((N + TC_BN - 1) / TC_BN) * ((M + 127) / 128);
+    // tokens per CTA: 128 while that still gives every SM at most one tile, 256 beyond (half the dequant work per MMA)
+    pl.BM = (M > 128 && tiles128 > sm_count()) ? 256 : 128;
+    pl.tiles = ((N + TC_BN - 1) / TC_BN) * ((M + pl.BM - 1) / pl.BM);
+    pl.stages = K / TC_KS;
+    // split-K when the tiles alone leave most SMs idle (M <= 128 on a 4096-column layer is 32 tiles): partial tiles in the
+    // caller's workspace, the CTA that draws the last ticket of a tile adds them up in split order
+    int splits = 1;
+    while (splits < 8 && pl.tiles * splits * 2 <= sm_count() && pl.stages / (splits * 2) >= 8) splits *= 2;
+    if (splits > 1) {
+        const size_t need = size_t(B200BIT_WS_TICKET_BYTES) + size_t(splits) * M * N * sizeof(float);
+        if (workspace_bytes < need || size_t(pl.tiles) * sizeof(unsigned) > B200BIT_WS_ZERO_OFFSET) splits = 1;
+    }
+    pl.splits = splits;
+    const int gs = K / G;
+    const int per_slice = (pl.stages + splits - 1) / splits;                   // most stages of one k-slice
+    const int span = (per_slice * TC_KS + gs - 1) / gs + 1;                    // groups such a range can touch
+    pl.Gs = span < G ? span : G;
+    pl.smem = size_t(TC_XSTAGES) * pl.BM * TC_KS * 2 + 256 + size_t(pl.Gs) * TC_BN * 2 +
+              (asym ? size_t(pl.Gs) * (TC_BN / (32 / w_bit)) * 4 : size_t(pl.Gs) * TC_BN * 2);
+    pl.fits = pl.smem <= size_t(227) * 1024;
+    return pl;
+}
+}  // namespace b200bit
+
+// 1 when b200bit_mpq_forward_tc runs this problem (shape rules + the group table of a k-slice fits shared memory)
+extern "C" int b200bit_mpq_forward_tc_supported(int M, int K, int N, int G, int w_bit, int asym, int dtype, size_t workspace_bytes) {
+    if (!((w_bit == 4 || w_bit == 2) && dtype == B200BIT_F16)) return 0;
+    if (!(M > 0 && K > 0 && N > 0 && G > 0 && K % G == 0 && K % TC_KS == 0 && N % 8 == 0 && (K / G) % 32 == 0)) return 0;
+    const int gs = K / G;
+    if ((gs & (gs - 1)) != 0) return 0;
+    if (asym && N % (32 / w_bit) != 0) return 0;
+    return tc_plan(M, K, N, G, w_bit, asym, workspace_bytes).fits ? 1 : 0;
+}
+
 // y[M,N] = x[M,K] @ dequant(qweight): 4-bit, f16, contiguous groups of 32*i values, K % 64 == 0, N % 8 == 0.
 extern "C" int b200bit_mpq_forward_tc(const void* x, const int32_t* qweight, const void* scales, const void* zeros, void* y,
                                       int M, int K, int N, int G, int w_bit, int asym, int dtype, void* workspace,
@@ -347,9 +393,9 @@ extern "C" int b200bit_mpq_forward_tc(const void* x, const int32_t* qweight, con
     B200_REQUIRE(M > 0 && K > 0 && N > 0 && G > 0 && K % G == 0 && K % TC_KS == 0 && N % 8 == 0 && (K / G) % 32 == 0, B200BIT_ERR_SHAPE,
                  "mpq_forward_tc: bad sizes M=%d K=%d N=%d G=%d (K %% 64 == 0, N %% 8 == 0, groups of 32*i)", M, K, N, G);
     B200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, B200BIT_ERR_ARG, "mpq_forward_tc: x must be 16-byte aligned");
-    // tokens per CTA: 128 while that still gives every SM at most one tile, 256 beyond (half the dequant work per MMA)
-    const int tiles128 = ((N + TC_BN - 1) / TC_BN) * ((M + 127) / 128);
-    const int BM = (M > 128 && tiles128 > sm_count()) ? 256 : 128;
+    const TcPlan pl = tc_plan(M, K, N, G, w_bit, asym, workspace ? workspace_bytes : 0);
+    B200_REQUIRE(pl.fits, B200BIT_ERR_UNSUPPORTED, "mpq_forward_tc: the %d groups of a k-slice do not fit the shared-memory parameter table", pl.Gs);
+    const int BM = pl.BM;
     CUtensorMap tm_x;
     int rc = make_map_2d(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, x, uint64_t(K), uint64_t(M), uint64_t(K) * 2, TC_KS, uint32_t(BM),
                          CU_TENSOR_MAP_SWIZZLE_128B);
@@ -363,8 +409,8 @@ extern "C" int b200bit_mpq_forward_tc(const void* x, const int32_t* qweight, con
     p.gs_shift = 0;
     while ((1 << p.gs_shift) < p.gs) ++p.gs_shift;
     B200_REQUIRE((1 << p.gs_shift) == p.gs, B200BIT_ERR_UNSUPPORTED, "mpq_forward_tc: group size %d is not a power of two", p.gs);
-    const size_t smem = size_t(TC_XSTAGES) * BM * TC_KS * 2 + 256 + size_t(G) * TC_BN * 2 + (asym ? size_t(G) * (TC_BN / (32 / w_bit)) * 4 : size_t(G) * TC_BN * 2);
-    B200_REQUIRE(smem <= 227 * 1024, B200BIT_ERR_UNSUPPORTED, "mpq_forward_tc: %d groups do not fit the shared-memory parameter table", G);
+    const size_t smem = pl.smem;
+    p.Gs = pl.Gs;
     static bool configured_dev[64] = {false};
     int dev = 0;
     B200_CUDA_OK(cudaGetDevice(&dev));
@@ -375,16 +421,7 @@ extern "C" int b200bit_mpq_forward_tc(const void* x, const int32_t* qweight, con
         B200_CUDA_OK(cudaFuncSetAttribute(mpq_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured_dev[dev & 63] = true;
     }
-    // split-K when the tiles alone leave most SMs idle (M <= 128 on a 4096-column layer is 32 tiles): partial tiles in the
-    // caller's workspace, the CTA that draws the last ticket of a tile adds them up in split order
-    const int tiles = ((N + TC_BN - 1) / TC_BN) * ((M + BM - 1) / BM);
-    const int stages = K / TC_KS;
-    int splits = 1;
-    while (splits < 8 && tiles * splits * 2 <= sm_count() && stages / (splits * 2) >= 8) splits *= 2;
-    if (splits > 1) {
-        const size_t need = size_t(B200BIT_WS_TICKET_BYTES) + size_t(splits) * M * N * sizeof(float);
-        if (!workspace || workspace_bytes < need || size_t(tiles) * sizeof(unsigned) > B200BIT_WS_ZERO_OFFSET) splits = 1;
-    }
+    const int splits = pl.splits;
     p.splits = splits;
     p.tickets = reinterpret_cast<unsigned*>(workspace);
     p.part = splits > 1 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B200BIT_WS_TICKET_BYTES) : nullptr;

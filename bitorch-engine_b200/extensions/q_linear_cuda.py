@@ -87,6 +87,18 @@ TC_MIN_ROWS = 16           # from 17 rows on the tcgen05 kernel takes every shap
 GRAD_INPUT_FUSED_MAX_ROWS = 4
 
 
+_tc_verdicts = {}
+
+
+def _tc_supported(M, K, N, G, w_bit, asym, ws_bytes):
+    """b200bit_mpq_forward_tc_supported, remembered per problem (shape rules + does the group table of a k-slice fit)."""
+    key = (M, K, N, G, w_bit, asym, ws_bytes)
+    v = _tc_verdicts.get(key)
+    if v is None:
+        v = _tc_verdicts[key] = bool(_cabi.lib().b200bit_mpq_forward_tc_supported(M, K, N, G, w_bit, int(asym), _cabi.F16, ws_bytes))
+    return v
+
+
 def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False):
     """y[M,N] = x[M,K] @ dequant(qweight)  (q_linear_cuda.cpp:258-270 -> mpq_linear_cuda_kernel.cu:603-626).
 
@@ -123,16 +135,16 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         # cuBLAS it is ahead at every M, profiles/r2_25_tc_kernel_split_k.jsonl).  Shapes it does not cover: the
         # small-batch kernels up to 32 rows (2-bit: 8), then dequantise ONCE (one kernel, bit-identical to unpack_qweight) +
         # dense GEMM -- the switch the reference makes at 32 rows (mpq_layer.py:59-63).
-        gs = K // G if G and K % G == 0 else 0
-        tc_ok = (w_bit in (2, 4) and x.dtype == torch.float16 and K % 64 == 0 and N % 8 == 0 and gs % 32 == 0 and gs > 0
-                 and gs & (gs - 1) == 0 and G * (512 if not asym else 320) <= 160 * 1024 and _gidx_is_trivial(g_idx, K, G))
+        ws_bytes = _cabi.WS_TICKET_BYTES + 8 * min(M, 256) * N * 4 if M <= 256 else 0
+        tc_ok = (w_bit in (2, 4) and x.dtype == torch.float16 and _gidx_is_trivial(g_idx, K, G) and
+                 _tc_supported(M, K, N, G, w_bit, bool(asym), ws_bytes))
         if tc_ok:
             x = x.contiguous()
             if x.data_ptr() % 16 == 0:
                 y = torch.empty((M, N), dtype=x.dtype, device=x.device)
                 with _on_device(x.device):
                     stream = _raw_stream(x.device)
-                    ws = _cabi.workspace(x.device, stream, _cabi.WS_TICKET_BYTES + 8 * min(M, 256) * N * 4 if M <= 256 else 0)
+                    ws = _cabi.workspace(x.device, stream, ws_bytes)
                     rc = _cabi.lib().b200bit_mpq_forward_tc(x.data_ptr(), qweight.contiguous().data_ptr(),
                                                             scales.contiguous().data_ptr(), zeros.contiguous().data_ptr(),
                                                             y.data_ptr(), M, K, N, G, w_bit, int(bool(asym)), _cabi.F16,

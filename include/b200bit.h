@@ -94,6 +94,8 @@ B200BIT_API int b200bit_mpq_forward(const void* x, const int32_t* qweight, const
  * mpq_layer.py:59-63), which this replaces without materialising the fp16 matrix.  2- / 4-bit, f16, contiguous groups of 32 * 2^i,
  * K % 64 == 0, N % 8 == 0, x 16-byte aligned.  b200bit_mpq_forward routes here for M > 16 (2-bit: M > 8) when the shape qualifies.
  * workspace (optional, as for b200bit_mpq_forward): enables split-K when the tiles alone would leave most SMs idle. */
+B200BIT_API int b200bit_mpq_forward_tc_supported(int M, int K, int N, int G, int w_bit, int asym, int dtype,
+                                                 size_t workspace_bytes);      /* 1: the call below runs this problem */
 B200BIT_API int b200bit_mpq_forward_tc(const void* x, const int32_t* qweight, const void* scales, const void* zeros, void* y,
                                        int M, int K, int N, int G, int w_bit, int asym, int dtype, void* workspace,
                                        size_t workspace_bytes, void* stream);
