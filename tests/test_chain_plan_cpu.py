@@ -138,3 +138,25 @@ def test_rejects_what_the_kernel_cannot_run():
     table = (_cabi.ChainPlanNode * 1)()
     info = (ctypes.c_int * 16)()
     assert lib.b200bit_mpq_chain_plan_host(arr, 1, 2, 0, _cabi.F16, table, info) != 0     # the chain is the 4-bit kernel
+
+
+def test_batched_kernel_support_predicate():
+    """b200bit_mpq_forward_tc_supported is pure host arithmetic (tile height, split-K factor, group-table rows of a k-slice);
+    the C dispatcher and the python shim both ask it.  148 SMs are assumed without a device."""
+    lib = _cabi.lib()
+
+    def ws(M, N):
+        return _cabi.WS_TICKET_BYTES + 8 * min(M, 256) * N * 4 if M <= 256 else 0
+
+    def ok(M, K, N, G, bits, asym=0, dtype=None, wsb=None):
+        return lib.b200bit_mpq_forward_tc_supported(M, K, N, G, bits, asym, _cabi.F16 if dtype is None else dtype,
+                                                    ws(M, N) if wsb is None else wsb)
+    assert ok(32, 4096, 4096, 32, 4) and ok(2048, 4096, 11008, 32, 4) and ok(512, 14336, 4096, 112, 4)
+    assert ok(32, 4096, 11008, 128, 2) and ok(33, 4096, 4096, 32, 4, asym=1)
+    # 2-bit g32, K = 11008: 344 groups x 128 columns x (scale, zero) do not fit as a whole (176 KB) -- with split-K (workspace,
+    # M <= 256) a slice touches 87 of them; without a workspace, or above 256 rows, the shape is declined
+    assert ok(32, 11008, 4096, 344, 2) and ok(256, 11008, 4096, 344, 2)
+    assert not ok(32, 11008, 4096, 344, 2, wsb=0) and not ok(512, 11008, 4096, 344, 2)
+    # shape rules
+    assert not ok(32, 4096, 4096, 32, 8) and not ok(32, 4096, 4096, 32, 4, dtype=_cabi.BF16)
+    assert not ok(32, 4096 + 32, 4096, 1, 4) and not ok(32, 4096, 4100, 32, 4) and not ok(32, 4096, 4096, 4096 // 96, 4)
