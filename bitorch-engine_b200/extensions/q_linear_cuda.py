@@ -88,6 +88,23 @@ GRAD_INPUT_FUSED_MAX_ROWS = 4
 
 
 _tc_verdicts = {}
+_sm_counts = {}
+TC_SPLIT_WS_CAP = 64 << 20
+
+
+def _tc_workspace_bytes(M, N, device):
+    """Split-K scratch for the batched kernel: fp32 partial tiles for up to 8 k-slices.  Always for small batches; for
+    larger ones only when the tiles alone would leave more than half of the SMs idle (narrow layers: the 1024-column k / v
+    projections of a GQA model at a 512-token prefill are 32 tiles) and the scratch stays under 64 MB."""
+    if M <= 256:
+        return _cabi.WS_TICKET_BYTES + 8 * M * N * 4
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    sms = _sm_counts.get(idx)
+    if sms is None:
+        sms = _sm_counts[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    tiles128 = -(-N // 128) * -(-M // 128)
+    need = _cabi.WS_TICKET_BYTES + 8 * M * N * 4
+    return need if (tiles128 * 2 <= sms and need <= TC_SPLIT_WS_CAP) else 0
 
 
 def _tc_supported(M, K, N, G, w_bit, asym, ws_bytes):
@@ -135,7 +152,7 @@ def mpq_forward(x, qweight, scales, zeros, g_idx, a_bit, w_bit, asym, pdl=False)
         # cuBLAS it is ahead at every M, profiles/r2_25_tc_kernel_split_k.jsonl).  Shapes it does not cover: the
         # small-batch kernels up to 32 rows (2-bit: 8), then dequantise ONCE (one kernel, bit-identical to unpack_qweight) +
         # dense GEMM -- the switch the reference makes at 32 rows (mpq_layer.py:59-63).
-        ws_bytes = _cabi.WS_TICKET_BYTES + 8 * min(M, 256) * N * 4 if M <= 256 else 0
+        ws_bytes = _tc_workspace_bytes(M, N, x.device)
         tc_ok = (w_bit in (2, 4) and x.dtype == torch.float16 and _gidx_is_trivial(g_idx, K, G) and
                  _tc_supported(M, K, N, G, w_bit, bool(asym), ws_bytes))
         if tc_ok:
